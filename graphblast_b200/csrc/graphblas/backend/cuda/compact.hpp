@@ -1,0 +1,37 @@
+// graphblast_b200 backend — host driver for the ordered compaction kernels
+// (kernels/compact.cuh).  Three launches and ONE 8-byte device-to-host read.
+#ifndef GRAPHBLAS_BACKEND_CUDA_COMPACT_HPP_
+#define GRAPHBLAS_BACKEND_CUDA_COMPACT_HPP_
+
+#include "graphblas/backend/cuda/util.hpp"
+#include "graphblas/backend/cuda/descriptor.hpp"
+#include "graphblas/backend/cuda/kernels/kernels.hpp"
+
+namespace graphblas {
+namespace backend {
+
+// Runs src over nitems items; returns the number of outputs emitted.
+template <typename Source>
+Index compactOrdered(Source src, Index nitems, Descriptor* desc) {
+  if (nitems <= 0) return 0;
+  const int nblocks = static_cast<int>(
+      (static_cast<long long>(nitems) + GB_COMPACT_NT - 1) / GB_COMPACT_NT);
+  int* block_counts = reinterpret_cast<int*>(
+      desc->scratch(GB_SCRATCH_BLOCKSUM, static_cast<size_t>(nblocks)*sizeof(int)));
+  unsigned long long* ctr = desc->counters() + 1;
+  cudaStream_t s = gbStream();
+  compactCountKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
+      block_counts);
+  GB_KERNEL_CHECK();
+  compactScanKernel<<<1, 1024, 0, s>>>(block_counts, nblocks, ctr);
+  GB_KERNEL_CHECK();
+  compactEmitKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
+      block_counts);
+  GB_KERNEL_CHECK();
+  return static_cast<Index>(runtime().fetch(ctr));
+}
+
+}  // namespace backend
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_BACKEND_CUDA_COMPACT_HPP_

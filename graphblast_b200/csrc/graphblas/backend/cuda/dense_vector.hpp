@@ -1,0 +1,464 @@
+// graphblast_b200 backend — DenseVector<T>: n values resident in HBM with a
+// lazily materialised host mirror.
+//
+// Replaces reference graphblas/backend/cuda/dense_vector.hpp:22-438 (same
+// public methods and the member names tests reach: nvals_, nnz_, h_val_,
+// d_val_, need_update_).  Differences by design:
+//  * device storage is allocated on first use, stream-ordered (util.hpp gbMalloc);
+//  * fill()/fillAscending() run on the device (the reference loops on the host
+//    and copies 4n bytes H2D, dense_vector.hpp:312-318);
+//  * setElement() writes one element (the reference round-trips the vector,
+//    dense_vector.hpp:225-230);
+//  * computeNnz() reuses a count left behind by the producing kernel when valid
+//    (nnz_valid_), otherwise one counting kernel + 8-byte read.
+//  * adopted device pointers (build(T*, n)) are never freed here.
+#ifndef GRAPHBLAS_BACKEND_CUDA_DENSE_VECTOR_HPP_
+#define GRAPHBLAS_BACKEND_CUDA_DENSE_VECTOR_HPP_
+
+#include <vector>
+#include <iostream>
+#include <unordered_set>
+
+#include "graphblas/backend/cuda/util.hpp"
+#include "graphblas/backend/cuda/descriptor.hpp"
+#include "graphblas/backend/cuda/kernels/kernels.hpp"
+
+namespace graphblas {
+namespace backend {
+
+template <typename T>
+class SparseVector;
+
+template <typename T>
+class DenseVector {
+ public:
+  DenseVector()
+      : nvals_(0), nnz_(0), h_val_(NULL), d_val_(NULL), need_update_(0),
+        owns_device_(true), nnz_valid_(false), nnz_identity_(T()),
+        d_count_(NULL), count_pending_(false), zero_one_(false) {}
+
+  explicit DenseVector(Index nsize)
+      : nvals_(nsize), nnz_(0), h_val_(NULL), d_val_(NULL), need_update_(0),
+        owns_device_(true), nnz_valid_(false), nnz_identity_(T()),
+        d_count_(NULL), count_pending_(false), zero_one_(false) {}
+
+  ~DenseVector();
+
+  // C API Methods
+  Info nnew(Index nsize);
+  Info dup(const DenseVector* rhs);
+  Info clear();
+  inline Info size(Index* nsize_) const;
+  inline Info nvals(Index* nvals_) const;
+  inline Info nnz(Index* nnz_) const;
+  Info computeNnz(Index* nnz, T identity, Descriptor* desc);
+  template <typename BinaryOpT>
+  Info build(const std::vector<Index>* indices,
+             const std::vector<T>*     values,
+             Index                     nvals,
+             BinaryOpT                 dup);
+  Info build(const std::vector<T>* values,
+             Index                 nvals);
+  Info build(T*    values,
+             Index nvals);
+  Info setElement(T val, Index index);
+  Info extractElement(T* val, Index index);
+  Info extractTuples(std::vector<Index>* indices,
+                     std::vector<T>*     values,
+                     Index*              n);
+  Info extractTuples(std::vector<T>* values,
+                     Index*          n);
+  // Raw D2H copy into caller memory (C-ABI path; no std::vector in between).
+  Info extractRaw(T* values, Index n);
+
+  // Handy methods
+  const T& operator[](Index ind);
+  Info resize(Index nsize);
+  Info fill(T val);
+  Info fillAscending(Index vals);
+  Info print(bool force_update = false);
+  Info countUnique(Index* count);
+  Info allocateCpu();
+  Info allocateGpu();
+  Info allocate();
+  Info cpuToGpu();
+  Info gpuToCpu(bool force_update = false);
+  Info swap(DenseVector* rhs);
+
+  // Marks the device copy as modified by a kernel.
+  inline void touched() {
+    need_update_ = true;
+    nnz_valid_ = false;
+    count_pending_ = false;
+    zero_one_ = false;
+  }
+
+ public:  // (private in the reference; its drivers `#define private public`)
+  Index nvals_;  // vector length
+  Index nnz_;
+  T*    h_val_;
+  T*    d_val_;
+
+  bool  need_update_;  // device copy newer than host copy
+  bool  owns_device_;
+  bool  nnz_valid_;    // nnz_ counts entries != nnz_identity_ of the current data
+  T     nnz_identity_;
+
+  // Count left on the device by the kernel that produced the current contents
+  // (fused Boolean pull): *d_count_ = #entries != nnz_identity_.
+  unsigned long long* d_count_;
+  bool  count_pending_;
+  bool  zero_one_;     // contents are exactly 0/1 (so a plus-reduce == count)
+
+  unsigned long long* countCell() {
+    if (d_count_ == NULL)
+      d_count_ = reinterpret_cast<unsigned long long*>(
+          gbMalloc(sizeof(unsigned long long)));
+    return d_count_;
+  }
+};
+
+template <typename T>
+DenseVector<T>::~DenseVector() {
+  if (h_val_ != NULL) free(h_val_);
+  if (d_val_ != NULL && owns_device_) gbFree(d_val_);
+  if (d_count_ != NULL) gbFree(d_count_);
+}
+
+template <typename T>
+Info DenseVector<T>::nnew(Index nsize) {
+  if (nsize != nvals_) {
+    if (h_val_ != NULL) { free(h_val_); h_val_ = NULL; }
+    if (d_val_ != NULL && owns_device_) gbFree(d_val_);
+    d_val_ = NULL;
+    owns_device_ = true;
+  }
+  nvals_ = nsize;
+  nnz_valid_ = false;
+  count_pending_ = false;
+  zero_one_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::dup(const DenseVector* rhs) {
+  if (nvals_ != rhs->nvals_) CHECK(nnew(rhs->nvals_));
+  CHECK(allocateGpu());
+  if (rhs->d_val_ != NULL && rhs->d_val_ != d_val_)
+    CUDA_CALL(cudaMemcpyAsync(d_val_, rhs->d_val_, nvals_*sizeof(T),
+        cudaMemcpyDeviceToDevice, gbStream()));
+  need_update_  = true;
+  nnz_valid_    = rhs->nnz_valid_;
+  nnz_          = rhs->nnz_;
+  nnz_identity_ = rhs->nnz_identity_;
+  count_pending_ = false;
+  zero_one_     = rhs->zero_one_;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::clear() {
+  CHECK(fill((T)0));
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+inline Info DenseVector<T>::size(Index* nsize_t) const {
+  *nsize_t = nvals_;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+inline Info DenseVector<T>::nvals(Index* nvals_t) const {
+  *nvals_t = nvals_;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+inline Info DenseVector<T>::nnz(Index* nnz_t) const {
+  *nnz_t = nnz_;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::computeNnz(Index* nnz_t, T identity, Descriptor* desc) {
+  if (nvals_ == 0) return GrB_INVALID_OBJECT;
+  if (nnz_valid_ && nnz_identity_ == identity) {
+    *nnz_t = nnz_;
+    return GrB_SUCCESS;
+  }
+  if (count_pending_ && nnz_identity_ == identity && d_count_ != NULL) {
+    nnz_ = static_cast<Index>(runtime().fetch(d_count_));
+    nnz_valid_ = true;
+    count_pending_ = false;
+    *nnz_t = nnz_;
+    return GrB_SUCCESS;
+  }
+  CHECK(allocateGpu());
+  unsigned long long* ctr = desc->counters();
+  CUDA_CALL(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), gbStream()));
+  countNonIdentityKernel<256><<<gridFor(nvals_, 256), 256, 0, gbStream()>>>(
+      ctr, d_val_, identity, nvals_);
+  GB_KERNEL_CHECK();
+  nnz_          = static_cast<Index>(runtime().fetch(ctr));
+  nnz_valid_    = true;
+  nnz_identity_ = identity;
+  *nnz_t = nnz_;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+template <typename BinaryOpT>
+Info DenseVector<T>::build(const std::vector<Index>* indices,
+                           const std::vector<T>*     values,
+                           Index                     nvals,
+                           BinaryOpT                 dup) {
+  std::cout << "DeVec Build Using Sparse Indices\n";
+  std::cout << "Error: Feature not implemented yet!\n";
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::build(const std::vector<T>* values,
+                           Index                 nvals) {
+  if (nvals > nvals_) return GrB_INDEX_OUT_OF_BOUNDS;
+  CHECK(allocate());
+  CHECK(gpuToCpu());
+  for (Index i = 0; i < nvals; i++) h_val_[i] = (*values)[i];
+  CHECK(cpuToGpu());
+  return GrB_SUCCESS;
+}
+
+// Adopts a device pointer; ownership stays with the caller.
+template <typename T>
+Info DenseVector<T>::build(T*    values,
+                           Index nvals) {
+  if (d_val_ != NULL && owns_device_) gbFree(d_val_);
+  if (h_val_ != NULL && nvals != nvals_) { free(h_val_); h_val_ = NULL; }
+  d_val_       = values;
+  nvals_       = nvals;
+  owns_device_ = false;
+  need_update_ = true;
+  nnz_valid_   = false;
+  count_pending_ = false;
+  zero_one_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::setElement(T val, Index index) {
+  if (index < 0 || index >= nvals_) return GrB_INDEX_OUT_OF_BOUNDS;
+  CHECK(allocateGpu());
+  T* stage = reinterpret_cast<T*>(runtime().h_pinned);
+  runtime().sync();              // staging slot may be in flight
+  *stage = val;
+  CUDA_CALL(cudaMemcpyAsync(d_val_ + index, stage, sizeof(T),
+      cudaMemcpyHostToDevice, gbStream()));
+  runtime().sync();
+  if (h_val_ != NULL && !need_update_) h_val_[index] = val;
+  nnz_valid_ = false;
+  count_pending_ = false;
+  zero_one_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::extractElement(T* val, Index index) {
+  if (index < 0 || index >= nvals_) return GrB_INDEX_OUT_OF_BOUNDS;
+  CHECK(allocateGpu());
+  *val = runtime().fetch(d_val_ + index);
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::extractTuples(std::vector<Index>* indices,
+                                   std::vector<T>*     values,
+                                   Index*              n) {
+  std::cout << "DeVec ExtractTuples into Sparse Indices\n";
+  std::cout << "Error: Feature not implemented yet!\n";
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::extractTuples(std::vector<T>* values, Index* n) {
+  values->clear();
+  if (*n > nvals_) {
+    std::cout << *n << " > " << nvals_ << std::endl;
+    std::cout << "Error: DeVec Too many tuples requested!\n";
+    return GrB_UNINITIALIZED_OBJECT;
+  }
+  if (*n < nvals_) {
+    std::cout << *n << " < " << nvals_ << std::endl;
+    std::cout << "Error: DeVec Insufficient space!\n";
+    return GrB_INSUFFICIENT_SPACE;
+  }
+  CHECK(gpuToCpu());
+  values->assign(h_val_, h_val_ + *n);
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::extractRaw(T* values, Index n) {
+  if (n > nvals_) return GrB_UNINITIALIZED_OBJECT;
+  if (n < nvals_) return GrB_INSUFFICIENT_SPACE;
+  CHECK(allocateGpu());
+  CUDA_CALL(cudaMemcpyAsync(values, d_val_, static_cast<size_t>(n)*sizeof(T),
+      cudaMemcpyDeviceToHost, gbStream()));
+  runtime().sync();
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+const T& DenseVector<T>::operator[](Index ind) {
+  static T zero = T();
+  if (gpuToCpu() != GrB_SUCCESS) return zero;
+  if (ind >= nvals_) {
+    std::cout << "Error: Index out of bounds!\n";
+    return zero;
+  }
+  return h_val_[ind];
+}
+
+template <typename T>
+Info DenseVector<T>::resize(Index nsize) {
+  T* d_old = d_val_;
+  bool old_owned = owns_device_;
+  Index to_copy = std::min(nsize, nvals_);
+  CHECK(gpuToCpu());
+  T* h_old = h_val_;
+  h_val_ = NULL;
+  d_val_ = NULL;
+  owns_device_ = true;
+  nvals_ = nsize;
+  CHECK(allocate());
+  if (h_old != NULL) memcpy(h_val_, h_old, to_copy*sizeof(T));
+  if (d_old != NULL)
+    CUDA_CALL(cudaMemcpyAsync(d_val_, d_old, to_copy*sizeof(T),
+        cudaMemcpyDeviceToDevice, gbStream()));
+  if (h_old != NULL) free(h_old);
+  if (d_old != NULL && old_owned) gbFree(d_old);
+  nnz_valid_ = false;
+  count_pending_ = false;
+  zero_one_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::fill(T val) {
+  if (nvals_ == 0) return GrB_SUCCESS;
+  CHECK(allocateGpu());
+  fillKernel<<<gridFor(nvals_, 256), 256, 0, gbStream()>>>(d_val_, val,
+      nvals_);
+  GB_KERNEL_CHECK();
+  need_update_ = true;
+  nnz_valid_   = false;
+  count_pending_ = false;
+  zero_one_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::fillAscending(Index nvals) {
+  if (nvals_ == 0) return GrB_SUCCESS;
+  CHECK(allocateGpu());
+  iotaKernel<<<gridFor(nvals_, 256), 256, 0, gbStream()>>>(d_val_, nvals_);
+  GB_KERNEL_CHECK();
+  need_update_ = true;
+  nnz_valid_   = false;
+  count_pending_ = false;
+  zero_one_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::print(bool force_update) {
+  CHECK(gpuToCpu(force_update));
+  printArray("val", h_val_, std::min(nvals_, 40));
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::countUnique(Index* count) {
+  CHECK(gpuToCpu());
+  std::unordered_set<Index> unique;
+  for (Index i = 0; i < nvals_; i++) unique.insert(h_val_[i]);
+  *count = unique.size();
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::allocateCpu() {
+  if (nvals_ > 0 && h_val_ == NULL) {
+    h_val_ = reinterpret_cast<T*>(malloc(static_cast<size_t>(nvals_)*sizeof(T)));
+    if (h_val_ == NULL) {
+      std::cout << "Error: CPU DeVec Out of memory!\n";
+      return GrB_OUT_OF_MEMORY;
+    }
+    if (d_val_ != NULL) need_update_ = true;
+  }
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::allocateGpu() {
+  if (nvals_ > 0 && d_val_ == NULL) {
+    d_val_ = reinterpret_cast<T*>(gbMalloc(static_cast<size_t>(nvals_)*sizeof(T)));
+    owns_device_ = true;
+    printMemory("DeVec");
+  }
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::allocate() {
+  CHECK(allocateCpu());
+  CHECK(allocateGpu());
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::cpuToGpu() {
+  CHECK(allocate());
+  CUDA_CALL(cudaMemcpyAsync(d_val_, h_val_, static_cast<size_t>(nvals_)*sizeof(T),
+      cudaMemcpyHostToDevice, gbStream()));
+  runtime().sync();
+  need_update_ = false;
+  nnz_valid_   = false;
+  count_pending_ = false;
+  zero_one_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::gpuToCpu(bool force_update) {
+  bool fresh_host = (h_val_ == NULL);
+  CHECK(allocate());
+  if (need_update_ || force_update || fresh_host) {
+    CUDA_CALL(cudaMemcpyAsync(h_val_, d_val_,
+        static_cast<size_t>(nvals_)*sizeof(T), cudaMemcpyDeviceToHost,
+        gbStream()));
+    runtime().sync();
+  }
+  need_update_ = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info DenseVector<T>::swap(DenseVector* rhs) {  // NOLINT(build/include_what_you_use)
+  std::swap(nvals_,        rhs->nvals_);
+  std::swap(nnz_,          rhs->nnz_);
+  std::swap(h_val_,        rhs->h_val_);
+  std::swap(d_val_,        rhs->d_val_);
+  std::swap(need_update_,  rhs->need_update_);
+  std::swap(owns_device_,  rhs->owns_device_);
+  std::swap(nnz_valid_,    rhs->nnz_valid_);
+  std::swap(nnz_identity_, rhs->nnz_identity_);
+  std::swap(d_count_,      rhs->d_count_);
+  std::swap(count_pending_, rhs->count_pending_);
+  std::swap(zero_one_,     rhs->zero_one_);
+  return GrB_SUCCESS;
+}
+}  // namespace backend
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_BACKEND_CUDA_DENSE_VECTOR_HPP_

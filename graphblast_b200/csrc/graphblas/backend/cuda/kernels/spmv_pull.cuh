@@ -1,0 +1,281 @@
+// graphblast_b200 backend — PULL direction kernels (dense frontier).
+//
+//  * spmvMergeKernel      : generic-semiring CSR SpMV, merge-path load balanced
+//                           (rows + nonzeros split evenly across CTAs and threads),
+//                           256-bit streaming loads of colind/val, gathers of the
+//                           dense vector served from L2 (evict-last), shuffle-based
+//                           segmented scan for rows that straddle threads, per-CTA
+//                           carry-out fixed up by spmvCarryFixupKernel.
+//                           Replaces mgpu::SpmvCsrBinary (reference spmv.hpp:188-190,
+//                           ext/moderngpu/include/kernels/spmvcsr.cuh:334-413,489-587:
+//                           5+ launches and 2 device syncs per SpMV).
+//  * spmvMaskedOrPullKernel: fused mask + OR-AND + early-exit + operand-reuse
+//                           Boolean pull (reference kernels/spmv.hpp:7-59), plus a
+//                           fused count of discovered rows so the direction switch
+//                           needs no extra pass.
+//
+// Algorithmic bytes per launch:
+//   merge SpMV : 4(n+1) rowptr + 8 nnz colind/val + 4n gather (once) + 4n write
+//   Boolean    : 4(n+1) + 4 E_inspected + 4n mask + 4n write
+#ifndef GRAPHBLAS_BACKEND_CUDA_KERNELS_SPMV_PULL_CUH_
+#define GRAPHBLAS_BACKEND_CUDA_KERNELS_SPMV_PULL_CUH_
+
+#include "graphblas/backend/cuda/kernels/common.cuh"
+
+namespace graphblas {
+namespace backend {
+
+#define GB_SPMV_NT   256
+#define GB_SPMV_IPT  7                               // merge items per thread
+#define GB_SPMV_TILE (GB_SPMV_NT*GB_SPMV_IPT)        // merge items per CTA
+
+// Merge-path split: on diagonal d (d = rows consumed + nonzeros consumed) return
+// the number of row-end items consumed.  List A is row_end[r] = rowptr[r+1],
+// list B the nonzero indices 0..nnz-1; a row-end is consumed before the nonzero
+// with the same value (that nonzero belongs to the next row).
+__device__ __forceinline__ Index mergePathRows(long long d,
+                                               const Index* __restrict__ rowptr,
+                                               Index nrows, Index nnz) {
+  long long lo = d - nnz; if (lo < 0) lo = 0;
+  long long hi = d < nrows ? d : nrows;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (static_cast<long long>(__ldg(rowptr + mid + 1)) <= d - mid - 1)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return static_cast<Index>(lo);
+}
+
+template <bool Vec256, typename W, typename a, typename U,
+          typename MulOp, typename AddOp>
+__global__ void __launch_bounds__(GB_SPMV_NT)
+spmvMergeKernel(W* __restrict__           w,
+                Index* __restrict__       carry_row,
+                W* __restrict__           carry_val,
+                const Index* __restrict__ rowptr,
+                const Index* __restrict__ colind,
+                const a* __restrict__     val,
+                const U* __restrict__     u,
+                Index                     nrows,
+                Index                     nnz,
+                W                         identity,
+                MulOp                     mul_op,
+                AddOp                     add_op) {
+  __shared__ Index s_rowend[GB_SPMV_TILE + 1];
+  __shared__ __align__(32) W s_prod[GB_SPMV_TILE + 16];
+  __shared__ W     s_out[GB_SPMV_TILE];
+  __shared__ Index s_wkey[GB_SPMV_NT/32];
+  __shared__ W     s_wval[GB_SPMV_NT/32];
+  __shared__ Index s_split[2];
+
+  const int t    = threadIdx.x;
+  const int lane = t & 31;
+  const int wid  = t >> 5;
+
+  const long long total = static_cast<long long>(nrows) + nnz;
+  const long long d0 = static_cast<long long>(blockIdx.x)*GB_SPMV_TILE;
+  long long d1 = d0 + GB_SPMV_TILE; if (d1 > total) d1 = total;
+
+  if (t == 0)  s_split[0] = mergePathRows(d0, rowptr, nrows, nnz);
+  if (t == 32) s_split[1] = mergePathRows(d1, rowptr, nrows, nnz);
+  __syncthreads();
+  const Index r0 = s_split[0];
+  const Index r1 = s_split[1];
+  const Index k0 = static_cast<Index>(d0 - r0);
+  const Index k1 = static_cast<Index>(d1 - r1);
+  const int   nr = r1 - r0;          // rows that END in this tile
+  const int   nk = k1 - k0;          // nonzeros consumed in this tile
+  const Index k0a = k0 & ~7;         // 32-byte aligned load window start
+
+  // Row-end offsets for rows r0 .. r1 (the last one is the still-open row).
+  for (int i = t; i <= nr; i += GB_SPMV_NT) {
+    Index r = r0 + i;
+    s_rowend[i] = (r < nrows) ? __ldg(rowptr + r + 1) : nnz;
+  }
+
+  // Products mul(A(k), u[col(k)]) for k in [k0, k1) into s_prod[k - k0a].
+  const uint64_t pol = makeEvictLastPolicy();
+  if (nk > 0) {
+    const int nchunks = (k1 - k0a + 7) >> 3;
+    for (int c = t; c < nchunks; c += GB_SPMV_NT) {
+      const Index kb = k0a + (c << 3);
+      Index cols[8];
+      W     prods[8];
+      if (Vec256 && kb + 8 <= nnz) {
+        Word8 cw = ldStream256(colind + kb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cols[j] = cw.w[j];
+        U uv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) uv[j] = ldGather(u + cols[j], pol);
+        Word8 vw = ldStream256(val + kb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a av;
+          memcpy(&av, &vw.w[j], 4);
+          prods[j] = mul_op(av, uv[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          Index k = kb + j;
+          if (k >= k0 && k < k1) {
+            Index col = ldStream(colind + k);
+            a av = ldStream(val + k);
+            prods[j] = mul_op(av, ldGather(u + col, pol));
+          } else {
+            prods[j] = identity;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_prod[(c << 3) + j] = prods[j];
+    }
+  }
+  __syncthreads();
+
+  // Thread-level merge path inside the tile.
+  int ld = t*GB_SPMV_IPT;
+  const int tile_items = static_cast<int>(d1 - d0);
+  if (ld > tile_items) ld = tile_items;
+  int lo = ld - nk; if (lo < 0) lo = 0;
+  int hi = ld < nr ? ld : nr;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (s_rowend[mid] <= k0 + (ld - mid - 1)) lo = mid + 1; else hi = mid;
+  }
+  int   i = lo;                       // local row
+  Index k = k0 + (ld - lo);           // global nonzero index
+  const int first_i = i;
+  W acc = identity;
+#pragma unroll
+  for (int it = 0; it < GB_SPMV_IPT; ++it) {
+    if (ld + it < tile_items) {
+      if (k < s_rowend[i]) {
+        acc = add_op(acc, s_prod[k - k0a]);
+        ++k;
+      } else {
+        s_out[i] = acc;
+        acc = identity;
+        ++i;
+      }
+    }
+  }
+
+  // Segmented inclusive scan of (key = open row, value = partial) over the CTA.
+  Index key = i;
+  W     v   = acc;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    Index pk = __shfl_up_sync(GB_FULL_MASK, key, off);
+    W     pv = __shfl_up_sync(GB_FULL_MASK, v, off);
+    if (lane >= off && pk == key) v = add_op(pv, v);
+  }
+  if (lane == 31) { s_wkey[wid] = key; s_wval[wid] = v; }
+  const Index key0 = __shfl_sync(GB_FULL_MASK, key, 0);
+  Index ekey = __shfl_up_sync(GB_FULL_MASK, key, 1);
+  W     eval = __shfl_up_sync(GB_FULL_MASK, v, 1);
+  __syncthreads();
+  // Fold the tails of the preceding warps.
+  Index ck = -1;
+  W     cv = identity;
+  for (int ww = 0; ww < wid; ++ww) {
+    Index wk = s_wkey[ww];
+    W     wv = s_wval[ww];
+    if (wk == ck) cv = add_op(cv, wv);
+    else { ck = wk; cv = wv; }
+  }
+  W carry_in;
+  if (lane == 0) {
+    carry_in = (ck == first_i) ? cv : identity;
+  } else {
+    carry_in = eval;                                 // ekey == first_i always
+    if (ekey == key0 && ck == ekey) carry_in = add_op(cv, eval);
+  }
+  (void)ekey;
+
+  if (i > first_i) s_out[first_i] = add_op(carry_in, s_out[first_i]);
+
+  if (t == GB_SPMV_NT - 1) {
+    W out = (i > first_i) ? acc : add_op(carry_in, acc);
+    carry_row[blockIdx.x] = (r0 + i < nrows) ? (r0 + i) : -1;
+    carry_val[blockIdx.x] = out;
+  }
+  __syncthreads();
+
+  for (int j = t; j < nr; j += GB_SPMV_NT) w[r0 + j] = s_out[j];
+}
+
+// One thread per CTA carry: the first carry of a run of equal rows folds the
+// whole run and adds it (on the left) to the row's stored tail.
+template <typename W, typename AddOp>
+__global__ void spmvCarryFixupKernel(W* __restrict__ w,
+                                     const Index* __restrict__ carry_row,
+                                     const W* __restrict__ carry_val,
+                                     int ncarry, AddOp add_op) {
+  int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= ncarry) return;
+  const Index row = carry_row[c];
+  if (row < 0) return;
+  if (c > 0 && carry_row[c-1] == row) return;
+  W total = carry_val[c];
+  for (int c2 = c + 1; c2 < ncarry && carry_row[c2] == row; ++c2)
+    total = add_op(total, carry_val[c2]);
+  w[row] = add_op(total, w[row]);
+}
+
+// ---------------------------------------------------------------------------
+// Fused masked Boolean pull.  One thread per row (rows with a satisfied mask
+// test are skipped without touching the matrix; unvisited rows stop at the
+// first frontier neighbour when early exit is on).
+// ---------------------------------------------------------------------------
+#define GB_PULL_NT 256
+
+template <bool UseScmp, bool UseEarlyExit, bool UseOpReuse,
+          typename W, typename M, typename U>
+__global__ void __launch_bounds__(GB_PULL_NT)
+spmvMaskedOrPullKernel(W* __restrict__           w,
+                       const M* __restrict__     mask,
+                       U                         identity,
+                       Index                     nrows,
+                       const Index* __restrict__ rowptr,
+                       const Index* __restrict__ colind,
+                       const U* __restrict__     u,
+                       unsigned long long*       discovered) {
+  __shared__ int s_red[GB_PULL_NT/32];
+  Index row = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  int found_total = 0;
+  for (; row < nrows; row += stride) {
+    bool found = false;
+    const M m = mask[row];
+    const bool masked_out = UseScmp ? (m != static_cast<M>(0))
+                                    : (m == static_cast<M>(0));
+    if (!masked_out) {
+      Index k   = rowptr[row];
+      Index end = rowptr[row + 1];
+      for (; k < end; ++k) {
+        const Index col = __ldg(colind + k);
+        bool hit;
+        if (UseOpReuse) hit = (__ldg(mask + col) != static_cast<M>(0));
+        else            hit = (__ldg(u + col) != identity);
+        if (hit) {
+          found = true;
+          if (UseEarlyExit) break;
+        }
+      }
+    }
+    w[row] = found ? static_cast<W>(1) : static_cast<W>(0);
+    found_total += found ? 1 : 0;
+  }
+  int total = blockSum<GB_PULL_NT>(found_total, s_red);
+  if (threadIdx.x == 0 && total)
+    atomicAdd(discovered, static_cast<unsigned long long>(total));
+}
+
+}  // namespace backend
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_BACKEND_CUDA_KERNELS_SPMV_PULL_CUH_

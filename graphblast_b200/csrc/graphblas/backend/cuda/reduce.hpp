@@ -1,0 +1,147 @@
+// graphblast_b200 backend — monoid reductions (vector -> scalar, matrix -> scalar,
+// matrix rows -> vector).
+//
+// Replaces reference graphblas/backend/cuda/reduce.hpp:13-145.  Kept behaviour:
+// an empty input returns the identity (:23-26); in struct-only mode a sparse
+// vector / matrix reduces to its entry count (:71-72, :87-88).
+// New: a dense 0/1 vector produced by the fused Boolean pull carries its count,
+// so a plus-reduce over it is one 8-byte read instead of a pass over 4n bytes.
+#ifndef GRAPHBLAS_BACKEND_CUDA_REDUCE_HPP_
+#define GRAPHBLAS_BACKEND_CUDA_REDUCE_HPP_
+
+#include <iostream>
+
+#include "graphblas/backend/cuda/kernels/kernels.hpp"
+
+namespace graphblas {
+namespace backend {
+
+template <typename T, typename U,
+          typename BinaryOpT, typename MonoidT>
+Info reduceCommon(T*          val,
+                  BinaryOpT   accum,
+                  MonoidT     op,
+                  const U*    d_val,
+                  Index       nvals,
+                  Descriptor* desc) {
+  if (nvals == 0) {
+    *val = op.identity();
+    return GrB_SUCCESS;
+  }
+  const int grid = gridFor(nvals, GB_REDUCE_NT, 4);
+  T* partials = reinterpret_cast<T*>(desc->scratch(GB_SCRATCH_BLOCKSUM,
+      (static_cast<size_t>(grid) + 1)*sizeof(T)));
+  T* d_out = partials + grid;
+  cudaStream_t s = gbStream();
+  reducePartialKernel<<<grid, GB_REDUCE_NT, 0, s>>>(partials, d_val, nvals, op,
+      static_cast<T>(op.identity()));
+  GB_KERNEL_CHECK();
+  reduceFinalKernel<<<1, GB_REDUCE_NT, 0, s>>>(d_out, partials, grid, op,
+      static_cast<T>(op.identity()));
+  GB_KERNEL_CHECK();
+  *val = runtime().fetch(d_out);
+  return GrB_SUCCESS;
+}
+
+// Dense vector
+template <typename T, typename U,
+          typename BinaryOpT, typename MonoidT>
+Info reduceInner(T*                     val,
+                 BinaryOpT              accum,
+                 MonoidT                op,
+                 const DenseVector<U>*  u,
+                 Descriptor*            desc) {
+  DenseVector<U>* u_t = const_cast<DenseVector<U>*>(u);
+  // plus-like monoid over a 0/1 vector == number of ones.
+  if (u_t->zero_one_ && op(3, 5) == 8 && op.identity() == static_cast<T>(0)) {
+    Index count;
+    CHECK(u_t->computeNnz(&count, static_cast<U>(0), desc));
+    *val = static_cast<T>(count);
+    return GrB_SUCCESS;
+  }
+  return reduceCommon(val, accum, op, u->d_val_, u->nvals_, desc);
+}
+
+// Sparse vector
+template <typename T, typename U,
+          typename BinaryOpT, typename MonoidT>
+Info reduceInner(T*                     val,
+                 BinaryOpT              accum,
+                 MonoidT                op,
+                 const SparseVector<U>* u,
+                 Descriptor*            desc) {
+  if (desc->struconly())
+    *val = u->nvals_;
+  else
+    return reduceCommon(val, accum, op, u->d_val_, u->nvals_, desc);
+  return GrB_SUCCESS;
+}
+
+// Sparse matrix -> scalar
+template <typename T, typename a,
+          typename BinaryOpT, typename MonoidT>
+Info reduceInner(T*                     val,
+                 BinaryOpT              accum,
+                 MonoidT                op,
+                 const SparseMatrix<a>* A,
+                 Descriptor*            desc) {
+  if (desc->struconly())
+    *val = A->nvals_;
+  else
+    return reduceCommon(val, accum, op, A->d_csrVal_, A->nvals_, desc);
+  return GrB_SUCCESS;
+}
+
+// Dense matrix -> vector: placeholder, as in the reference (:94-104)
+template <typename W, typename a, typename M,
+          typename BinaryOpT,     typename MonoidT>
+Info reduceInner(DenseVector<W>*       w,
+                 const Vector<M>*      mask,
+                 BinaryOpT             accum,
+                 MonoidT               op,
+                 const DenseMatrix<a>* A,
+                 Descriptor*           desc) {
+  std::cout << "Error: Dense reduce matrix-to-vector not implemented yet!\n";
+  return GrB_SUCCESS;
+}
+
+// Sparse matrix rows -> dense vector
+template <typename W, typename a, typename M,
+          typename BinaryOpT,     typename MonoidT>
+Info reduceInner(DenseVector<W>*        w,
+                 const Vector<M>*       mask,
+                 BinaryOpT              accum,
+                 MonoidT                op,
+                 const SparseMatrix<a>* A,
+                 Descriptor*            desc) {
+  if (desc->struconly()) {
+    // The reference leaves w untouched here (:123-124).
+  } else {
+    if (A->nrows_ == 0) return GrB_INVALID_OBJECT;
+    CHECK(w->allocateGpu());
+    reduceRowsKernel<<<gridFor(static_cast<size_t>(A->nrows_)*32, 256), 256, 0,
+        gbStream()>>>(w->d_val_, A->d_csrRowPtr_, A->d_csrVal_, A->nrows_, op,
+        static_cast<W>(op.identity()));
+    GB_KERNEL_CHECK();
+    w->touched();
+    w->nnz_ = A->nrows_;
+  }
+  return GrB_SUCCESS;
+}
+
+// Dense matrix -> scalar: placeholder, as in the reference (:147-156)
+template <typename T, typename a,
+          typename BinaryOpT,     typename MonoidT>
+Info reduceInner(T*                    val,
+                 BinaryOpT             accum,
+                 MonoidT               op,
+                 const DenseMatrix<a>* A,
+                 Descriptor*           desc) {
+  std::cout << "Error: Dense reduce matrix-to-scalar not implemented yet!\n";
+  return GrB_SUCCESS;
+}
+
+}  // namespace backend
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_BACKEND_CUDA_REDUCE_HPP_

@@ -1,0 +1,199 @@
+// graphblast_b200 backend — pull-direction mxv host: w = A' (+.x) u with a dense
+// u, A' = CSR rows of A, or CSC columns of A when the descriptor says transposed
+// (vxm toggles GrB_INP1, so vxm pulls over the CSC).
+//
+// Replaces reference graphblas/backend/cuda/spmv.hpp:20-236.  Same decision:
+//   mask given, --fusedmask 1 and the semiring's add is logical-or
+//   (add_op(3,5) == 1, reference :84-96)  -> fused masked Boolean kernel;
+//   otherwise                              -> generic merge-path SpMV, then the
+//   mask pass that writes identity where masked out (:203-212), then the accum
+//   pass that combines with the semiring's ADD (:213-219 — the reference ignores
+//   the accum functor itself).
+#ifndef GRAPHBLAS_BACKEND_CUDA_SPMV_HPP_
+#define GRAPHBLAS_BACKEND_CUDA_SPMV_HPP_
+
+#include <iostream>
+#include <string>
+
+#include "graphblas/backend/cuda/kernels/kernels.hpp"
+
+namespace graphblas {
+namespace backend {
+
+// Generic SpMV into `out` (raw result, no mask/accum).  2 launches.
+template <typename W, typename a, typename U, typename SemiringT>
+Info spmvMergeLaunch(W*           out,
+                     SemiringT    op,
+                     const Index* rowptr,
+                     const Index* colind,
+                     const a*     val,
+                     const U*     u,
+                     Index        nrows,
+                     Index        nnz,
+                     Descriptor*  desc) {
+  if (nrows <= 0) return GrB_SUCCESS;
+  const long long total = static_cast<long long>(nrows) + nnz;
+  const int nctas = static_cast<int>((total + GB_SPMV_TILE - 1)/GB_SPMV_TILE);
+  Index* carry_row = reinterpret_cast<Index*>(desc->scratch(
+      GB_SCRATCH_CARRY_ROW, static_cast<size_t>(nctas)*sizeof(Index)));
+  W* carry_val = reinterpret_cast<W*>(desc->scratch(
+      GB_SCRATCH_CARRY_VAL, static_cast<size_t>(nctas)*sizeof(W)));
+  cudaStream_t s = gbStream();
+
+  const bool aligned =
+      (reinterpret_cast<uintptr_t>(colind) % 32 == 0) &&
+      (reinterpret_cast<uintptr_t>(val)    % 32 == 0) &&
+      sizeof(a) == 4 && sizeof(Index) == 4;
+  if (aligned)
+    spmvMergeKernel<true><<<nctas, GB_SPMV_NT, 0, s>>>(out, carry_row,
+        carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
+        extractMul(op), extractAdd(op));
+  else
+    spmvMergeKernel<false><<<nctas, GB_SPMV_NT, 0, s>>>(out, carry_row,
+        carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
+        extractMul(op), extractAdd(op));
+  GB_KERNEL_CHECK();
+  spmvCarryFixupKernel<<<(nctas + 255)/256, 256, 0, s>>>(out, carry_row,
+      carry_val, nctas, extractAdd(op));
+  GB_KERNEL_CHECK();
+  return GrB_SUCCESS;
+}
+
+template <typename W, typename a, typename U, typename M,
+          typename BinaryOpT,      typename SemiringT>
+Info spmv(DenseVector<W>*        w,
+          const Vector<M>*       mask,
+          BinaryOpT              accum,
+          SemiringT              op,
+          const SparseMatrix<a>* A,
+          const DenseVector<U>*  u,
+          Descriptor*            desc) {
+  // Get descriptor parameters for SCMP, REPL, TRAN
+  Desc_value scmp_mode, repl_mode, inp0_mode, inp1_mode;
+  CHECK(desc->get(GrB_MASK, &scmp_mode));
+  CHECK(desc->get(GrB_OUTP, &repl_mode));
+  CHECK(desc->get(GrB_INP0, &inp0_mode));
+  CHECK(desc->get(GrB_INP1, &inp1_mode));
+
+  const bool use_mask  = (mask != NULL);
+  const bool use_accum = !AccumIsNull<BinaryOpT>::value;
+  const bool use_scmp  = (scmp_mode == GrB_SCMP);
+  const bool use_repl  = (repl_mode == GrB_REPLACE);
+  const bool use_tran  = (inp0_mode == GrB_TRAN || inp1_mode == GrB_TRAN);
+
+  if (desc->debug()) {
+    std::cout << "Executing Spmv\n";
+    printState(use_mask, use_accum, use_scmp, use_repl, use_tran);
+  }
+
+  // Transpose (default is CSR):
+  const Index* A_csrRowPtr = (use_tran) ? A->d_cscColPtr_ : A->d_csrRowPtr_;
+  const Index* A_csrColInd = (use_tran) ? A->d_cscRowInd_ : A->d_csrColInd_;
+  const a*     A_csrVal    = (use_tran) ? A->d_cscVal_    : A->d_csrVal_;
+  const Index  A_nrows     = (use_tran) ? A->ncols_       : A->nrows_;
+  if (A_csrRowPtr == NULL) return GrB_UNINITIALIZED_OBJECT;
+
+  DenseVector<U>* u_t = const_cast<DenseVector<U>*>(u);
+  CHECK(w->allocateGpu());
+  CHECK(u_t->allocateGpu());
+
+  // Which atomic the semiring's add behaves like (reference spmv.hpp:76-85).
+  auto add_op = extractAdd(op);
+  int functor = add_op(3, 5);
+
+  if (desc->struconly() && functor != 1)
+    std::cout << "Warning: Using structure-only mode and not using logical or "
+        << "semiring may result in unintended behaviour. Is this intended?\n";
+
+  cudaStream_t s = gbStream();
+
+  if (use_mask && desc->fusedmask() && functor == 1) {
+    Storage mask_vec_type;
+    CHECK(mask->getStorage(&mask_vec_type));
+
+    if (mask_vec_type == GrB_DENSE) {
+      const M* mask_val = mask->dense_.d_val_;
+      unsigned long long* ctr = w->countCell();
+      CUDA_CALL(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+      const int grid = gridFor(A_nrows, GB_PULL_NT, 8);
+
+      int variant = 0;
+      variant |= use_scmp          ? 4 : 0;
+      variant |= desc->earlyexit() ? 2 : 0;
+      variant |= desc->opreuse()   ? 1 : 0;
+
+#define GB_LAUNCH_PULL(SC, EE, OR)                                           \
+      spmvMaskedOrPullKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(        \
+          w->d_val_, mask_val, op.identity(), A_nrows, A_csrRowPtr,          \
+          A_csrColInd, u_t->d_val_, ctr)
+      switch (variant) {
+        case 0: GB_LAUNCH_PULL(false, false, false); break;
+        case 1: GB_LAUNCH_PULL(false, false, true ); break;
+        case 2: GB_LAUNCH_PULL(false, true,  false); break;
+        case 3: GB_LAUNCH_PULL(false, true,  true ); break;
+        case 4: GB_LAUNCH_PULL(true,  false, false); break;
+        case 5: GB_LAUNCH_PULL(true,  false, true ); break;
+        case 6: GB_LAUNCH_PULL(true,  true,  false); break;
+        case 7: GB_LAUNCH_PULL(true,  true,  true ); break;
+        default: break;
+      }
+#undef GB_LAUNCH_PULL
+      GB_KERNEL_CHECK();
+      w->touched();
+      // The kernel wrote 0/1 and counted the ones: the next convert() or
+      // a PlusMonoid reduce can reuse the count (one 8-byte read, no pass).
+      w->count_pending_ = true;
+      w->zero_one_      = true;
+      w->nnz_identity_  = static_cast<W>(0);
+      if (desc->debug())
+        printDevice("w_val", w->d_val_, A_nrows);
+    } else if (mask_vec_type == GrB_SPARSE) {
+      std::cout << "DeVec Sparse Mask logical_or Spmv\n";
+      std::cout << "Error: Feature not implemented yet!\n";
+    } else {
+      return GrB_UNINITIALIZED_OBJECT;
+    }
+  } else {
+    W* w_val;
+    if (use_accum)
+      w_val = reinterpret_cast<W*>(desc->scratch(GB_SCRATCH_VEC_A,
+          static_cast<size_t>(A_nrows)*sizeof(W)));
+    else
+      w_val = w->d_val_;
+
+    CHECK(spmvMergeLaunch(w_val, op, A_csrRowPtr, A_csrColInd, A_csrVal,
+        u_t->d_val_, A_nrows, A->nvals_, desc));
+
+    if (use_mask) {
+      Storage mask_vec_type;
+      CHECK(mask->getStorage(&mask_vec_type));
+      if (mask_vec_type != GrB_DENSE) {
+        std::cout << "Spmv generic semiring with sparse mask\n";
+        std::cout << "Error: Feature not implemented yet!\n";
+        return GrB_NOT_IMPLEMENTED;
+      }
+      const int grid = gridFor(A_nrows, 256);
+      // GrB_SCMP keeps entries whose mask is zero: overwrite where mask != 0.
+      if (use_scmp)
+        assignDenseDenseMaskKernel<false><<<grid, 256, 0, s>>>(w_val, A_nrows,
+            mask->dense_.d_val_, static_cast<W>(op.identity()));
+      else
+        assignDenseDenseMaskKernel<true><<<grid, 256, 0, s>>>(w_val, A_nrows,
+            mask->dense_.d_val_, static_cast<W>(op.identity()));
+      GB_KERNEL_CHECK();
+    }
+    if (use_accum) {
+      ewiseBinaryDenseKernel<<<gridFor(A_nrows, 256), 256, 0, s>>>(w->d_val_,
+          extractAdd(op), w->d_val_, w_val, A_nrows);
+      GB_KERNEL_CHECK();
+    }
+    w->touched();
+    if (desc->debug())
+      printDevice("w_val", w->d_val_, A_nrows);
+  }
+  return GrB_SUCCESS;
+}
+}  // namespace backend
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_BACKEND_CUDA_SPMV_HPP_

@@ -1,0 +1,207 @@
+// graphblast_b200 backend — error macros, debug printing, GpuTimer and the
+// per-process runtime context (stream, SM count, pinned staging).
+//
+// Replaces reference graphblas/backend/cuda/util.hpp:4-120.  Algorithm headers
+// include this file by literal path (reference graphblas/algorithm/bfs.hpp:8)
+// and use backend::GpuTimer {Start, Stop, ElapsedMillis}.
+//
+// Difference from the reference by design: CUDA_CALL checks the API status but
+// does NOT cudaThreadSynchronize() after every call (reference util.hpp:12-19);
+// the backend synchronises only where the host consumes a device result.
+#ifndef GRAPHBLAS_BACKEND_CUDA_UTIL_HPP_
+#define GRAPHBLAS_BACKEND_CUDA_UTIL_HPP_
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+
+#define CUDA_SAFE_CALL_NO_SYNC(call) do {                                    \
+  cudaError_t gb_err__ = (call);                                             \
+  if (cudaSuccess != gb_err__) {                                             \
+    fprintf(stderr, "Cuda error in file '%s' in line %i : %s.\n",            \
+            __FILE__, __LINE__, cudaGetErrorString(gb_err__));               \
+    exit(EXIT_FAILURE);                                                      \
+  } } while (0)
+
+#define CUDA_CALL(call) CUDA_SAFE_CALL_NO_SYNC(call)
+
+// After a kernel launch: catches launch-configuration errors immediately.
+#define GB_KERNEL_CHECK() CUDA_SAFE_CALL_NO_SYNC(cudaGetLastError())
+
+namespace graphblas {
+namespace backend {
+
+// ---------------------------------------------------------------------------
+// Runtime context: one per process (one process per GPU).
+// ---------------------------------------------------------------------------
+struct Runtime {
+  cudaStream_t stream;      // every backend kernel / copy is issued here
+  int          device;
+  int          sm_count;
+  void*        h_pinned;    // pinned staging for small D2H results
+  size_t       h_pinned_bytes;
+  bool         ready;
+
+  Runtime() : stream(0), device(0), sm_count(148), h_pinned(NULL),
+              h_pinned_bytes(0), ready(false) {}
+
+  void init() {
+    if (ready) return;
+    CUDA_CALL(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    CUDA_CALL(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    h_pinned_bytes = 4096;
+    CUDA_CALL(cudaMallocHost(&h_pinned, h_pinned_bytes));
+    ready = true;
+  }
+
+  // Blocking read of a small device value through pinned memory.
+  template <typename T>
+  T fetch(const T* d_ptr) {
+    init();
+    CUDA_CALL(cudaMemcpyAsync(h_pinned, d_ptr, sizeof(T),
+        cudaMemcpyDeviceToHost, stream));
+    CUDA_CALL(cudaStreamSynchronize(stream));
+    return *reinterpret_cast<T*>(h_pinned);
+  }
+
+  template <typename T>
+  void fetch2(const T* d_ptr, T* a, T* b) {
+    init();
+    CUDA_CALL(cudaMemcpyAsync(h_pinned, d_ptr, 2*sizeof(T),
+        cudaMemcpyDeviceToHost, stream));
+    CUDA_CALL(cudaStreamSynchronize(stream));
+    *a = reinterpret_cast<T*>(h_pinned)[0];
+    *b = reinterpret_cast<T*>(h_pinned)[1];
+  }
+
+  void sync() { CUDA_CALL(cudaStreamSynchronize(stream)); }
+};
+
+inline Runtime& runtime() {
+  static Runtime rt;
+  if (!rt.ready) rt.init();
+  return rt;
+}
+
+inline cudaStream_t gbStream() { return runtime().stream; }
+
+// Stream-ordered device allocation (cudaMallocAsync on the backend stream, pool
+// release threshold raised so freed blocks are reused without a device sync).
+// The reference allocates with cudaMalloc/cudaFree inside every algorithm call
+// (frontier vectors in algorithm/bfs.hpp:25-26); here that costs microseconds.
+inline void* gbMalloc(size_t bytes) {
+  static bool pool_ready = false;
+  Runtime& rt = runtime();
+  if (!pool_ready) {
+    cudaMemPool_t pool;
+    CUDA_CALL(cudaDeviceGetDefaultMemPool(&pool, rt.device));
+    unsigned long long threshold = ~0ull;
+    CUDA_CALL(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold,
+        &threshold));
+    pool_ready = true;
+  }
+  void* p = NULL;
+  if (bytes == 0) bytes = 16;
+  CUDA_CALL(cudaMallocAsync(&p, bytes, rt.stream));
+  return p;
+}
+
+inline void gbFree(void* p) {
+  // Errors ignored on purpose: destructors may run during context teardown.
+  if (p != NULL) (void)cudaFreeAsync(p, runtime().stream);
+}
+
+// Grid sizing helper: a grid-stride launch sized in whole waves of the SM count.
+inline int gridFor(size_t work_items, int threads, int ctas_per_sm = 8) {
+  size_t want = (work_items + threads - 1) / threads;
+  size_t cap  = static_cast<size_t>(runtime().sm_count) * ctas_per_sm;
+  if (want < 1) want = 1;
+  return static_cast<int>(want < cap ? want : cap);
+}
+
+inline void printMemory(const char* str) {
+  size_t free_b, total_b;
+  if (GrB_MEMORY) {
+    CUDA_CALL(cudaMemGetInfo(&free_b, &total_b));
+    std::cout << str << ": " << free_b << " bytes left out of " << total_b
+              << " bytes\n";
+  }
+}
+
+template <typename T>
+void printDevice(const char* str, const T* array, int length = 40,
+                 bool limit = true) {
+  if (limit && length > 40) length = 40;
+  if (length <= 0 || array == NULL) {
+    std::cout << str << ": (empty)\n";
+    return;
+  }
+  T* temp = reinterpret_cast<T*>(malloc(length*sizeof(T)));
+  CUDA_CALL(cudaMemcpyAsync(temp, array, length*sizeof(T),
+      cudaMemcpyDeviceToHost, gbStream()));
+  runtime().sync();
+  printArray(str, temp, length, limit);
+  if (temp) free(temp);
+}
+
+inline void printState(bool use_mask, bool use_accum, bool use_scmp,
+                       bool use_repl, bool use_tran) {
+  std::cout << "Mask: " << use_mask  << std::endl;
+  std::cout << "Accum:" << use_accum << std::endl;
+  std::cout << "SCMP: " << use_scmp  << std::endl;
+  std::cout << "Repl: " << use_repl  << std::endl;
+  std::cout << "Tran: " << use_tran  << std::endl;
+}
+
+template <typename T> constexpr
+T const& min(T const& a, T const& b) {
+  return a < b ? a : b;
+}
+
+template <typename T> constexpr
+T const& max(T const& a, T const& b) {  // NOLINT(build/include_what_you_use)
+  return a > b ? a : b;
+}
+
+// "accum is GrB_NULL" test.  The reference decides this at run time from
+// typeid(accum).name().size() > 1 (reference spmv.hpp:34-40): GrB_NULL is NULL,
+// whose type mangles to a single character.  Same rule, decided at compile time.
+template <typename BinaryOpT>
+struct AccumIsNull {
+  static const bool value = std::is_integral<BinaryOpT>::value ||
+                            std::is_pointer<BinaryOpT>::value ||
+                            std::is_same<BinaryOpT, std::nullptr_t>::value;
+};
+
+struct GpuTimer {
+  cudaEvent_t start;
+  cudaEvent_t stop;
+
+  GpuTimer() {
+    cudaEventCreate(&start);
+    cudaEventCreate(&stop);
+  }
+
+  ~GpuTimer() {
+    cudaEventDestroy(start);
+    cudaEventDestroy(stop);
+  }
+
+  void Start() { cudaEventRecord(start, gbStream()); }
+  void Stop()  { cudaEventRecord(stop,  gbStream()); }
+
+  float ElapsedMillis() {
+    float elapsed;
+    cudaEventSynchronize(stop);
+    cudaEventElapsedTime(&elapsed, start, stop);
+    return elapsed;
+  }
+};
+
+}  // namespace backend
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_BACKEND_CUDA_UTIL_HPP_

@@ -1,0 +1,390 @@
+// graphblast_b200 backend — Vector<T>: dual-storage (sparse list / dense array)
+// vector whose storage follows the traversal direction.
+//
+// Replaces reference graphblas/backend/cuda/vector.hpp:27-454.  The direction
+// heuristic in convert() is the reference's (vector.hpp:292-323): with
+// ratio = nnz/size, sparse->dense when ratio > switchpoint and growing,
+// dense->sparse when ratio <= switchpoint and shrinking, otherwise remember ratio_.
+// Conversions run as device kernels: sparse->dense = fill + scatter,
+// dense->sparse = ordered compaction (kernels/compact.cuh).
+#ifndef GRAPHBLAS_BACKEND_CUDA_VECTOR_HPP_
+#define GRAPHBLAS_BACKEND_CUDA_VECTOR_HPP_
+
+#include <vector>
+#include <iostream>
+#include <algorithm>
+
+#include "graphblas/backend/cuda/util.hpp"
+#include "graphblas/backend/cuda/descriptor.hpp"
+#include "graphblas/backend/cuda/kernels/kernels.hpp"
+#include "graphblas/backend/cuda/compact.hpp"
+#include "graphblas/backend/cuda/sparse_vector.hpp"
+#include "graphblas/backend/cuda/dense_vector.hpp"
+
+namespace graphblas {
+namespace backend {
+
+template <typename T>
+class Vector {
+ public:
+  Vector()
+      : nsize_(0), nvals_(0), sparse_(0), dense_(0), vec_type_(GrB_UNKNOWN),
+        ratio_(0) {}
+  explicit Vector(Index nsize)
+      : nsize_(nsize), nvals_(0), sparse_(nsize), dense_(nsize),
+        vec_type_(GrB_UNKNOWN), ratio_(0) {}
+
+  ~Vector() {}
+
+  // C API Methods
+  Info nnew(Index nsize_t);
+  Info dup(const Vector* rhs);
+  Info clear();
+  Info size(Index* nsize_t);
+  Info nvals(Index* nvals_t);
+  template <typename BinaryOpT>
+  Info build(const std::vector<Index>* indices,
+             const std::vector<T>*     values,
+             Index                     nvals,
+             BinaryOpT                 dup);
+  Info build(const std::vector<T>* values,
+             Index                 nvals);
+  Info build(Index* indices,
+             T*     values,
+             Index nvals);
+  Info build(T*    values,
+             Index nvals);
+  Info setElement(T val, Index index);
+  Info extractElement(T* val, Index index);
+  Info extractTuples(std::vector<Index>* indices,
+                     std::vector<T>*     values,
+                     Index*              n);
+  Info extractTuples(std::vector<T>* values, Index* n);
+
+  // handy methods
+  const T& operator[](Index ind);
+  Info resize(Index nvals);
+  Info fill(T val);
+  Info fillAscending(Index nvals);
+  Info print(bool force_update = false);
+  Info countUnique(Index* count);
+  inline Info setStorage(Storage  vec_type);
+  inline Info getStorage(Storage* vec_type) const;
+  Info convert(T identity, float switchpoint, Descriptor* desc);
+  Info sparse2dense(T identity, Descriptor* desc = NULL);
+  Info dense2sparse(T identity, Descriptor* desc);
+  Info swap(Vector* rhs);
+
+ public:  // (private in the reference; its drivers `#define private public`)
+  Index           nsize_;
+  Index           nvals_;
+  SparseVector<T> sparse_;
+  DenseVector<T>  dense_;
+  Storage         vec_type_;
+
+  float           ratio_;  // nnz/size seen at the previous convert()
+};
+
+template <typename T>
+Info Vector<T>::nnew(Index nsize_t) {
+  nsize_ = nsize_t;
+  CHECK(sparse_.nnew(nsize_t));
+  CHECK(dense_.nnew(nsize_t));
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::dup(const Vector* rhs) {
+  vec_type_ = rhs->vec_type_;
+  if (vec_type_ == GrB_SPARSE)
+    return sparse_.dup(&rhs->sparse_);
+  else if (vec_type_ == GrB_DENSE)
+    return dense_.dup(&rhs->dense_);
+  std::cout << "Error: Failed to call dup!\n";
+  return GrB_UNINITIALIZED_OBJECT;
+}
+
+template <typename T>
+Info Vector<T>::clear() {
+  vec_type_ = GrB_UNKNOWN;
+  nvals_    = 0;
+  CHECK(sparse_.clear());
+  // dense_.clear() zero-fills in the reference; storage is unknown after
+  // clear(), so the fill is deferred until a storage is chosen.
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::size(Index* nsize_t) {
+  Index nsize;
+  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.size(&nsize));
+  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.size(&nsize));
+  else                              nsize = nsize_;
+  nsize_   = nsize;
+  *nsize_t = nsize;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::nvals(Index* nvals_t) {
+  Index new_nvals;
+  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.nvals(&new_nvals));
+  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.nvals(&new_nvals));
+  else                              new_nvals = nvals_;
+  nvals_   = new_nvals;
+  *nvals_t = new_nvals;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+template <typename BinaryOpT>
+Info Vector<T>::build(const std::vector<Index>* indices,
+                      const std::vector<T>*     values,
+                      Index                     nvals,
+                      BinaryOpT                 dup) {
+  vec_type_ = GrB_SPARSE;
+  return sparse_.build(indices, values, nvals, dup);
+}
+
+template <typename T>
+Info Vector<T>::build(const std::vector<T>* values,
+                      Index                 nvals) {
+  vec_type_ = GrB_DENSE;
+  return dense_.build(values, nvals);
+}
+
+template <typename T>
+Info Vector<T>::build(Index* indices,
+                      T*     values,
+                      Index nvals) {
+  vec_type_ = GrB_SPARSE;
+  return sparse_.build(indices, values, nvals);
+}
+
+template <typename T>
+Info Vector<T>::build(T*    values,
+                      Index nvals) {
+  vec_type_ = GrB_DENSE;
+  return dense_.build(values, nvals);
+}
+
+template <typename T>
+Info Vector<T>::setElement(T val, Index index) {
+  if (vec_type_ == GrB_SPARSE)      return sparse_.setElement(val, index);
+  else if (vec_type_ == GrB_DENSE)  return dense_.setElement(val, index);
+  return GrB_UNINITIALIZED_OBJECT;
+}
+
+template <typename T>
+Info Vector<T>::extractElement(T* val, Index index) {
+  if (vec_type_ == GrB_SPARSE)      return sparse_.extractElement(val, index);
+  else if (vec_type_ == GrB_DENSE)  return dense_.extractElement(val, index);
+  return GrB_UNINITIALIZED_OBJECT;
+}
+
+template <typename T>
+Info Vector<T>::extractTuples(std::vector<Index>* indices,
+                              std::vector<T>*     values,
+                              Index*              n) {
+  if (vec_type_ == GrB_SPARSE)
+    return sparse_.extractTuples(indices, values, n);
+  else if (vec_type_ == GrB_DENSE)
+    return dense_.extractTuples(indices, values, n);
+  return GrB_UNINITIALIZED_OBJECT;
+}
+
+// A sparse vector is densified with fill value 0 first (reference :208-217).
+template <typename T>
+Info Vector<T>::extractTuples(std::vector<T>* values,
+                              Index*          n) {
+  if (vec_type_ == GrB_SPARSE) {
+    CHECK(sparse2dense(0.f));
+    return dense_.extractTuples(values, n);
+  } else if (vec_type_ == GrB_DENSE) {
+    return dense_.extractTuples(values, n);
+  }
+  return GrB_UNINITIALIZED_OBJECT;
+}
+
+template <typename T>
+const T& Vector<T>::operator[](Index ind) {
+  static T zero = T();
+  if (vec_type_ == GrB_SPARSE)      return sparse_[ind];
+  else if (vec_type_ == GrB_DENSE)  return dense_[ind];
+  return zero;
+}
+
+template <typename T>
+Info Vector<T>::resize(Index nvals) {
+  if (vec_type_ == GrB_SPARSE)      return sparse_.resize(nvals);
+  else if (vec_type_ == GrB_DENSE)  return dense_.resize(nvals);
+  return GrB_UNINITIALIZED_OBJECT;
+}
+
+template <typename T>
+Info Vector<T>::fill(T val) {
+  if (vec_type_ != GrB_DENSE)
+    CHECK(setStorage(GrB_DENSE));
+  return dense_.fill(val);
+}
+
+template <typename T>
+Info Vector<T>::fillAscending(Index nvals) {
+  if (vec_type_ != GrB_DENSE)
+    CHECK(setStorage(GrB_DENSE));
+  return dense_.fillAscending(nvals);
+}
+
+template <typename T>
+Info Vector<T>::print(bool force_update) {
+  if (vec_type_ == GrB_SPARSE)      return sparse_.print(force_update);
+  else if (vec_type_ == GrB_DENSE)  return dense_.print(force_update);
+  std::cout << "Error: Vector not initialized!\n";
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::countUnique(Index* count) {
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+inline Info Vector<T>::setStorage(Storage vec_type) {
+  vec_type_ = vec_type;
+  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.allocateGpu());
+  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.allocateGpu());
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+inline Info Vector<T>::getStorage(Storage* vec_type) const {
+  *vec_type = vec_type_;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::convert(T identity, float switchpoint, Descriptor* desc) {
+  Index nvals_t;
+  Index nsize_t;
+  if (vec_type_ == GrB_SPARSE) {
+    CHECK(sparse_.nvals(&nvals_t));
+    CHECK(sparse_.size(&nsize_t));
+  } else if (vec_type_ == GrB_DENSE) {
+    CHECK(dense_.computeNnz(&nvals_t, identity, desc));
+    CHECK(dense_.nvals(&nsize_t));
+  } else {
+    return GrB_UNINITIALIZED_OBJECT;
+  }
+
+  float ratio = static_cast<float>(nvals_t)/nsize_t;
+  if (desc->dirinfo())
+    std::cout << "Nnz ratio: " << ratio << " Switch point: "
+        << switchpoint << std::endl;
+
+  if (vec_type_ == GrB_SPARSE) {
+    if (ratio > switchpoint && ratio > ratio_)
+      CHECK(sparse2dense(identity, desc));
+    else
+      ratio_ = ratio;
+  } else if (vec_type_ == GrB_DENSE) {
+    if (ratio <= switchpoint && ratio < ratio_)
+      CHECK(dense2sparse(identity, desc));
+    else
+      ratio_ = ratio;
+  }
+  return GrB_SUCCESS;
+}
+
+// With --opreuse the dense array is left untouched: the fused Boolean pull reads
+// the mask instead of the frontier (reference vector.hpp:344-357).
+template <typename T>
+Info Vector<T>::sparse2dense(T identity, Descriptor* desc) {
+  if (vec_type_ == GrB_DENSE) return GrB_SUCCESS;
+  if (vec_type_ == GrB_UNKNOWN) {
+    CHECK(setStorage(GrB_DENSE));
+    return GrB_SUCCESS;
+  }
+
+  if (desc != NULL && desc->dirinfo())
+    std::cout << "Converting from sparse to dense!\n";
+
+  CHECK(setStorage(GrB_DENSE));
+  const Index nvals = sparse_.nvals_;
+
+  if (desc == NULL || !desc->opreuse()) {
+    CHECK(dense_.fill(identity));
+    if (nvals > 0) {
+      const int nt = 256;
+      if (desc != NULL && desc->struconly())
+        scatterConstKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
+            dense_.d_val_, sparse_.d_ind_, (T)1, nvals);
+      else
+        scatterValsKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
+            dense_.d_val_, sparse_.d_ind_, sparse_.d_val_, nvals);
+      GB_KERNEL_CHECK();
+    }
+  }
+
+  vec_type_            = GrB_DENSE;
+  dense_.need_update_  = true;
+  dense_.nnz_          = nvals;
+  dense_.nnz_valid_    = false;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::dense2sparse(T identity, Descriptor* desc) {
+  if (vec_type_ == GrB_SPARSE) return GrB_INVALID_OBJECT;
+
+  if (desc->dirinfo())
+    std::cout << "Converting from dense to sparse!\n";
+
+  CHECK(dense_.allocateGpu());
+  CHECK(sparse_.allocateGpu());
+  const Index n = dense_.nvals_;
+  const Index nitems = (n + 7)/8;
+
+  LoadBalanceMode mxv_mode = getEnv("GRB_LOAD_BALANCE_MODE",
+      GrB_LOAD_BALANCE_MERGE);
+
+  Index count;
+  if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
+    DenseCompactSource<T, true> src;
+    src.u = dense_.d_val_; src.identity = identity; src.n = n;
+    src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+    count = compactOrdered(src, nitems, desc);
+  } else {
+    DenseCompactSource<T, false> src;
+    src.u = dense_.d_val_; src.identity = identity; src.n = n;
+    src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+    count = compactOrdered(src, nitems, desc);
+  }
+  sparse_.nvals_ = count;
+
+  if (desc->debug()) {
+    std::cout << "Dense frontier size: " << n << std::endl;
+    std::cout << "Sparse frontier size: " << sparse_.nvals_ << std::endl;
+  }
+
+  vec_type_ = GrB_SPARSE;
+  sparse_.need_update_ = true;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::swap(Vector* rhs) {  // NOLINT(build/include_what_you_use)
+  if (vec_type_ != rhs->vec_type_ || vec_type_ == GrB_UNKNOWN)
+    return GrB_INVALID_OBJECT;
+
+  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.swap(&rhs->sparse_));
+  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.swap(&rhs->dense_));
+
+  std::swap(nsize_, rhs->nsize_);
+  std::swap(nvals_, rhs->nvals_);
+  std::swap(ratio_, rhs->ratio_);
+  return GrB_SUCCESS;
+}
+}  // namespace backend
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_BACKEND_CUDA_VECTOR_HPP_
