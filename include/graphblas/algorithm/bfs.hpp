@@ -1,0 +1,74 @@
+// graphblast_b200 — breadth-first search as a loop of GraphBLAS operations.
+//
+// Operation sequence per level is the reference's (graphblas/algorithm/bfs.hpp:46-79):
+//   assign(v<f1> = level) ; vxm(f2<!v> = f1 (||.&&) A) ; swap(f1,f2) ;
+//   succ = reduce(+, f1) ; stop when succ == 0.
+// Output convention: level of the source is 1, unreached vertices stay 0.
+// Returns the device time of the loop in milliseconds ("tight" in the reference
+// drivers), excluding the initial fill of v.
+#ifndef GRAPHBLAS_ALGORITHM_BFS_HPP_
+#define GRAPHBLAS_ALGORITHM_BFS_HPP_
+
+#include <string>
+#include <vector>
+
+#include "graphblas/algorithm/common.hpp"
+
+namespace graphblas {
+namespace algorithm {
+
+inline float bfs(Vector<float>*       v,
+                 const Matrix<float>* A,
+                 Index                s,
+                 Descriptor*          desc) {
+  Index n;
+  CHECK(A->nrows(&n));
+  CHECK(v->fill(0.f));
+
+  Vector<float> frontier(n);
+  Vector<float> next(n);
+
+  Desc_value mxv_mode;
+  CHECK(desc->get(GrB_MXVMODE, &mxv_mode));
+  if (mxv_mode == GrB_PULLONLY) {
+    CHECK(frontier.fill(0.f));
+    CHECK(frontier.setElement(1.f, s));
+  } else {
+    std::vector<Index> src_ind(1, s);
+    std::vector<float> src_val(1, 1.f);
+    CHECK(frontier.build(&src_ind, &src_val, 1, GrB_NULL));
+  }
+
+  backend::Descriptor& d = desc->descriptor_;
+  const bool verbose = (d.timing_ == 1);
+  LoopTimer clock(verbose);
+  float succ = 0.f;
+  Index unvisited = n;
+  clock.begin();
+
+  for (int level = 1; level <= d.max_niter_; ++level) {
+    unvisited -= static_cast<int>(succ);
+    assign<float, float, float, Index>(v, &frontier, GrB_NULL,
+        static_cast<float>(level), GrB_ALL, n, desc);
+    CHECK(desc->toggle(GrB_MASK));
+    vxm<float, float, float, float>(&next, v, GrB_NULL,
+        LogicalOrAndSemiring<float>(), &frontier, A, desc);
+    CHECK(desc->toggle(GrB_MASK));
+    CHECK(next.swap(&frontier));
+    reduce<float, float>(&succ, GrB_NULL, PlusMonoid<float>(), &frontier, desc);
+
+    if (verbose) {
+      float ms = clock.lap();
+      std::cout << level << ", " << succ << "/" << n << ", " << unvisited
+                << ", " << (d.lastmxv_ == GrB_PUSHONLY ? "push" : "pull")
+                << ", " << ms << "\n";
+    }
+    if (succ == 0) break;
+  }
+  return clock.finish();
+}
+
+}  // namespace algorithm
+}  // namespace graphblas
+
+#endif  // GRAPHBLAS_ALGORITHM_BFS_HPP_

@@ -5,6 +5,7 @@
 //   graphblas/algorithm/test_pr.hpp:15-80    SimpleReferencePr
 //   graphblas/algorithm/test_tc.hpp:41-85    SimpleReferenceTc
 //   graphblas/util.hpp:364-430, 502-556      readMtx (+removeSelfloop, customSort), coo2csr
+//   graphblas/algorithm/common.hpp:22-42     set_uniform_random (SSSP weights)
 // These four functions are what every reference driver runs and compares the
 // GPU result against (example/gbfs.cu:82,93 ...), i.e. the reference's
 // "CPU sequential backend".  This file only adds extern "C" entry points.
@@ -35,6 +36,7 @@
 #include "graphblas/algorithm/test_sssp.hpp"
 #include "graphblas/algorithm/test_pr.hpp"
 #include "graphblas/algorithm/test_tc.hpp"
+#include "graphblas/algorithm/common.hpp"
 
 namespace {
 // The reference functions print progress lines and array dumps to stdout;
@@ -58,6 +60,7 @@ struct QuietStdout {
 };
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 int ref_bfs(int nrows, const int* rowptr, const int* colind, int* levels,
@@ -103,4 +106,17 @@ int ref_load_mtx(const char* path, int directed, int* nrows_out, int* rowptr,
   return nvals;
 }
 
+// The SSSP edge-weight stream of reference example/gsssp.cu:75-84: the
+// set_uniform_random functor (graphblas/algorithm/common.hpp:22-42) configured
+// through GRB_SEED / GRB_UNIFORM_START / GRB_UNIFORM_END, applied n times.
+int ref_uniform_weights(int seed, int lo, int hi, long long n, float* out) {
+  setenv("GRB_SEED", std::to_string(seed).c_str(), 1);
+  setenv("GRB_UNIFORM_START", std::to_string(lo).c_str(), 1);
+  setenv("GRB_UNIFORM_END", std::to_string(hi).c_str(), 1);
+  graphblas::set_uniform_random<float> draw;
+  for (long long i = 0; i < n; ++i) out[i] = draw(0.f);
+  return 0;
+}
+
 }  // extern "C"
+#pragma GCC visibility pop

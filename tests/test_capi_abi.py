@@ -1,0 +1,101 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every
+symbol include/graphblast_b200.h declares; the Python mirror's enums equal the
+header's; compute entry points refuse to run without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import graphblast_b200 as gb
+from graphblast_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "graphblast_b200.h")).read()
+
+
+def declared_symbols():
+    return sorted(set(re.findall(r"\b(gb200_[a-z0-9_]+)\s*\(", HEADER)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 55
+    for name in names:
+        assert hasattr(lib, name), "missing export: " + name
+
+
+def test_python_binding_covers_every_declared_symbol():
+    bound = {s[0] for s in _lib.SIGNATURES}
+    assert bound == set(declared_symbols())
+
+
+def test_semiring_and_monoid_order_matches_header():
+    block = HEADER[HEADER.index("GB200_LOGICAL_OR_AND"):HEADER.index("GB200_NSEMIRINGS")]
+    names = re.findall(r"GB200_([A-Z_]+)", block)
+    want = [re.sub(r"(?<!^)(?=[A-Z])", "_", s.name).upper() for s in gb.Semiring]
+    assert names == want
+    block = HEADER[HEADER.index("GB200_PLUS_MONOID"):HEADER.index("GB200_NMONOIDS")]
+    names = [n[:-len("_MONOID")] for n in re.findall(r"GB200_([A-Z_]+)", block)]
+    want = [re.sub(r"(?<!^)(?=[A-Z])", "_", m.name).upper() for m in gb.Monoid]
+    assert names == want
+
+
+def test_descriptor_enum_values_match_reference_layout():
+    # GrB_SCMP=0, GrB_REPLACE=1, GrB_TRAN=2 is what Descriptor::toggle relies on
+    assert int(gb.Desc_value.GrB_SCMP) == 0
+    assert int(gb.Desc_value.GrB_REPLACE) == 1
+    assert int(gb.Desc_value.GrB_TRAN) == 2
+    assert int(gb.Desc_value.GrB_DEFAULT) == 3
+    assert [int(v) for v in (gb.Desc_value.GrB_PUSHPULL,
+                             gb.Desc_value.GrB_PUSHONLY,
+                             gb.Desc_value.GrB_PULLONLY)] == [10, 11, 12]
+    assert int(gb.Info.GrB_NOT_IMPLEMENTED) == 9 and int(gb.Info.GrB_PANIC) == 14
+
+
+def test_descriptor_host_logic_without_device():
+    """Descriptor set/get/toggle and the flag defaults are host-only."""
+    d = gb.Descriptor()
+    assert d.get(gb.Desc_field.GrB_MASK) == gb.Desc_value.GrB_DEFAULT
+    d.toggle(gb.Desc_field.GrB_MASK)
+    assert d.get(gb.Desc_field.GrB_MASK) == gb.Desc_value.GrB_SCMP
+    d.toggle(gb.Desc_field.GrB_MASK)
+    assert d.get(gb.Desc_field.GrB_MASK) == gb.Desc_value.GrB_DEFAULT
+    d.toggle(gb.Desc_field.GrB_INP1)
+    assert d.get(gb.Desc_field.GrB_INP1) == gb.Desc_value.GrB_TRAN
+    d.toggle(gb.Desc_field.GrB_OUTP)
+    assert d.get(gb.Desc_field.GrB_OUTP) == gb.Desc_value.GrB_REPLACE
+    # parseArgs defaults (reference util.hpp:39-132)
+    assert d.get_knob("mxvmode") == 1
+    assert d.get(gb.Desc_field.GrB_MXVMODE) == gb.Desc_value.GrB_PUSHONLY
+    assert d.get_knob("switchpoint") == pytest.approx(0.01)
+    assert d.get_knob("earlyexit") == 1 and d.get_knob("fusedmask") == 1
+    assert d.get_knob("sort") == 1 and d.get_knob("struconly") == 0
+    assert d.get_knob("max_niter") == 10000
+    d.set_knob("mxvmode", 0)
+    assert d.get(gb.Desc_field.GrB_MXVMODE) == gb.Desc_value.GrB_PUSHPULL
+    with pytest.raises(gb.GraphBLASError):
+        d.set_knob("mxvmode", 7)
+    with pytest.raises(gb.GraphBLASError):
+        d.set_knob("no_such_knob", 1)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(gb.GraphBLASError) as e:
+        gb.Vector(8)
+    assert e.value.info == gb.Info.GrB_PANIC
+    with pytest.raises(gb.GraphBLASError):
+        gb.Matrix(4, 4)
+    with pytest.raises(gb.GraphBLASError):
+        gb.init(0)
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.ExtensionMissing):
+        _lib.load()
