@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the direction-optimised mxv/vxm path.
+
+Metric (BASELINE.json): MTEPS = stored entries of A / time of one full traversal,
+direction-optimised BFS (LogicalOrAnd vxm, push SpMSpV <-> pull SpMV) on an R-MAT
+scale-24 edge-factor-16 graph (configs[2]), with the reference's benchmark flags
+(run_bfs.sh:8-27: --mxvmode 0 --struconly 1 --opreuse 1 --earlyexit 1).
+`--algo sssp` runs the MinimumPlus SSSP on the same graph instead
+(run_sssp.sh:15-32 flags), `--algo pr` PageRank, `--algo tc` triangle counting.
+
+A "step" is one full traversal from the same source.  One JSON line on stdout:
+  value       device-timed, graph resident in HBM, K steps between CUDA events
+  e2e         the same traversal through the public API with a host result buffer:
+              source id H2D + traversal + D2H of the n-float result, every step
+  roofline    the dominant hot kernel: algorithmic bytes / CUDA-event time, against
+              the measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU BFS (oracle/_ref) or the oracle port, one
+              traversal of the same graph on one host core
+
+`--impl reference` times the reference's CPU implementation of the same traversal
+instead (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", default="bfs", choices=["bfs", "sssp", "pr", "tc"])
+    ap.add_argument("--scale", type=int,
+                    default=int(os.environ.get("GB200_BENCH_SCALE", "24")))
+    ap.add_argument("--edgefactor", type=int, default=16)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,"
+             "clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_graph(args, torch, gb, graphs):
+    """R-MAT on the device with the reference loader's semantics (undirected,
+    no self-loops, no duplicates, sorted rows)."""
+    n = 1 << args.scale
+    src, dst = graphs.rmat_edges(args.scale, args.edgefactor, seed=args.seed)
+    rowptr, colind = graphs.build_csr(n, src, dst, undirected=True)
+    del src, dst
+    torch.cuda.empty_cache()
+    return n, rowptr, colind
+
+
+def cpu_bfs_baseline(h_rowptr, h_colind, source):
+    import oracle_binding as orc
+    if orc.ref() is not None:
+        kind, fn = "reference", orc.ref_bfs
+    else:
+        kind, fn = "port", orc.bfs
+    t0 = time.perf_counter()
+    levels = fn(h_rowptr, h_colind, source)
+    dt = time.perf_counter() - t0
+    return kind, dt, levels
+
+
+def run_reference_arm(args):
+    """The reference's CPU implementation (SimpleReferenceBfs / Sssp, built from
+    the reference sources into oracle/_ref; oracle port when that is absent) on
+    the same graph and source; one traversal per step, single host thread (the
+    reference's CPU code is sequential)."""
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import graphblast_b200 as gb
+    from graphblast_b200 import graphs
+    import oracle_binding as orc
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    gb.init(int(os.environ.get("LOCAL_RANK", "0")))
+    n, rowptr, colind = build_graph(args, torch, gb, graphs)
+    h_rp = rowptr.cpu().numpy()
+    h_ci = colind.cpu().numpy()
+    nnz = int(h_ci.shape[0])
+    source = int(np.argmax(np.diff(h_rp)))
+    del rowptr, colind
+    kind = "reference" if orc.ref() is not None else "port"
+    if args.algo == "sssp":
+        w = gb.api.host_uniform_weights(args.seed, 1, 64, nnz)
+        step = (lambda: orc.ref_sssp(h_rp, h_ci, w, source)) if kind == "reference" \
+            else (lambda: orc.sssp(h_rp, h_ci, w, source))
+    else:
+        step = (lambda: orc.ref_bfs(h_rp, h_ci, source)) if kind == "reference" \
+            else (lambda: orc.bfs(h_rp, h_ci, source))
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    ms = dt * 1e3 / args.steps
+    mteps = nnz / (ms * 1e3)
+    out = {
+        "impl": "reference",
+        "metric": "MTEPS", "value": mteps, "unit": "MTEPS (edges/s x 1e-6)",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n, nnz, source),
+        "cpu_baseline": {"value": mteps, "unit": "MTEPS", "cores": 1,
+                         "kind": kind,
+                         "sample": "one full traversal of the same graph per step"},
+        "e2e": {"value": mteps, "unit": "MTEPS", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, n, nnz, source):
+    names = {"bfs": "direction-optimised BFS (LogicalOrAnd vxm, push<->pull)",
+             "sssp": "SSSP (MinimumPlus vxm, push<->pull)",
+             "pr": "PageRank (PlusMultiplies vxm, 10 iterations)",
+             "tc": "triangle count (masked mxm on tril)"}
+    return {"workload": "%s on R-MAT scale-%d ef-%d (a,b,c,d)=(.57,.19,.19,.05) "
+                        "seed %d, symmetrised, no self-loops/duplicates"
+                        % (names[args.algo], args.scale, args.edgefactor,
+                           args.seed),
+            "n": n, "nnz": nnz, "source": source,
+            "flags": "--mxvmode 0 --struconly 1 --opreuse 1 --earlyexit 1"
+                     if args.algo == "bfs" else "--mxvmode 0",
+            "l2_policy": "inputs larger than L2 (graph arrays >> 126 MB)",
+            "partition": "1-D row slices" if args.gpus > 1 else "single GPU"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import graphblast_b200 as gb
+    from graphblast_b200 import algorithm, graphs, _lib
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    gb.init(local_rank)
+    lib = _lib.load()
+
+    if world > 1:
+        from graphblast_b200 import dist as gdist
+        result = gdist.bench_distributed(args, world, rank, local_rank)
+        if rank == 0:
+            print(json.dumps(result), flush=True)
+        return
+
+    n, rowptr, colind = build_graph(args, torch, gb, graphs)
+    nnz = int(colind.numel())
+    deg = rowptr[1:] - rowptr[:-1]
+    source = int(torch.argmax(deg).item())
+
+    desc_flags = dict(mxvmode=0)
+    if args.algo == "bfs":
+        desc_flags.update(struconly=1, opreuse=1, earlyexit=1)
+    if args.algo == "sssp":
+        desc_flags.update(switchpoint=0.025)
+    if args.algo == "pr":
+        desc_flags.update(max_niter=10)
+    desc = gb.Descriptor(**desc_flags)
+
+    keep = []
+    if args.algo == "bfs":
+        A = graphs.matrix_from_csr(n, rowptr, colind)
+    elif args.algo in ("sssp", "pr"):
+        if args.algo == "sssp":
+            w = gb.api.host_uniform_weights(args.seed, 1, 64, nnz)
+            d_w = torch.from_numpy(w).cuda()
+        else:
+            d_w = torch.ones(nnz, dtype=torch.float32, device="cuda")
+        d_wt = graphs.transpose_values(n, rowptr, colind, d_w)
+        A = graphs.matrix_from_csr(n, rowptr, colind, d_w, cscval=d_wt)
+        keep += [d_w, d_wt]
+        if args.algo == "pr":
+            A.pr_normalize(0.85, desc)
+    else:
+        h_rp = rowptr.cpu().numpy()
+        h_ci = colind.cpu().numpy()
+        import oracle_binding as orc_build
+        lr, lc = orc_build.tril(h_rp, h_ci)
+        d_lr = torch.from_numpy(lr).cuda()
+        d_lc = torch.from_numpy(lc).cuda()
+        A = graphs.matrix_from_csr(n, d_lr, d_lc, dtype=gb.api.INT32,
+                                   symmetric=False,
+                                   cscval=torch.ones(len(lc), dtype=torch.int32,
+                                                     device="cuda"))
+        keep += [d_lr, d_lc]
+        B = gb.Matrix(n, n, dtype=gb.api.INT32)
+
+    result_vec = gb.Vector(n)
+    tc_count = [0]
+
+    def step():
+        if args.algo == "bfs":
+            algorithm.bfs(result_vec, A, source, desc)
+        elif args.algo == "sssp":
+            algorithm.sssp(result_vec, A, source, desc)
+        elif args.algo == "pr":
+            algorithm.pr(result_vec, A, 0.85, 1e-8, desc)
+        else:
+            tc_count[0] = algorithm.tc(A, B, desc)[0]
+
+    # ---- warm-up ---------------------------------------------------------
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- device-timed region -----------------------------------------------
+    launches0 = C.c_ulonglong(0)
+    lib.gb200_launch_count(C.byref(launches0))
+    lib.gb200_profile_enable(1)
+    lib.gb200_profile_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = ev0.elapsed_time(ev1)
+    launches1 = C.c_ulonglong(0)
+    lib.gb200_launch_count(C.byref(launches1))
+    ms_per_step = total_ms / args.steps
+    mteps = nnz / (ms_per_step * 1e3)
+
+    kinds = ["spmvMergeKernel (merge-path pull SpMV)",
+             "spmvMaskedOrPullKernel (fused Boolean pull)",
+             "spmspvPushKernel (push SpMSpV expand)",
+             "spgemmMaskedKernel (masked dot-product SpGEMM)"]
+    prof = []
+    for k in range(4):
+        ms, ln, by = C.c_double(0), C.c_longlong(0), C.c_double(0)
+        lib.gb200_profile_read(k, C.byref(ms), C.byref(ln), C.byref(by))
+        prof.append((ms.value, ln.value, by.value))
+    lib.gb200_profile_enable(0)
+    dom = max(range(4), key=lambda k: prof[k][0])
+    peak, peak_src = measured_peak_hbm()
+    dom_ms, dom_launches, dom_bytes = prof[dom]
+    achieved = (dom_bytes / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
+    roofline = {
+        "kernel": kinds[dom], "bound": "hbm",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak if peak else None,
+        "peak_source": peak_src,
+        "launches": dom_launches,
+        "bytes_per_launch": dom_bytes / dom_launches if dom_launches else 0,
+        "ms_per_launch": dom_ms / dom_launches if dom_launches else 0,
+        "share_of_step": dom_ms / total_ms if total_ms else 0,
+        "traffic": None,
+        "all_kernels": {kinds[k]: {"ms": prof[k][0], "launches": prof[k][1],
+                                   "alg_bytes": prof[k][2]} for k in range(4)},
+    }
+
+    # ---- end-to-end through the public API, host buffers -----------------------
+    host_out = torch.empty(n, dtype=torch.float32).pin_memory()
+    host_src = torch.tensor([source], dtype=torch.int32).pin_memory()
+    dev_src = torch.empty(1, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_src.copy_(host_src, non_blocking=True)           # H2D: step input
+        s = int(dev_src.item()) if args.algo in ("bfs", "sssp") else source
+        if args.algo == "bfs":
+            algorithm.bfs(result_vec, A, s, desc)
+        elif args.algo == "sssp":
+            algorithm.sssp(result_vec, A, s, desc)
+        else:
+            step()
+        if args.algo != "tc":
+            result_vec.extract_into(host_out)                # D2H: step result
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e = {"value": nnz / (e2e_ms * 1e3), "unit": "MTEPS",
+           "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": 4,
+           "d2h_bytes_per_step": 4 * n if args.algo != "tc" else 8,
+           "note": "graph resident (built once, like the reference's "
+                   "Matrix::build before its timed loop); per step: source id "
+                   "H2D, traversal, n-float result D2H into pinned memory"}
+
+    # ---- CPU baseline: the reference's own CPU code on one host core -------------
+    cpu_baseline = None
+    parity = None
+    if not args.no_cpu_baseline:
+        h_rp = rowptr.cpu().numpy()
+        h_ci = colind.cpu().numpy()
+        if args.algo == "bfs":
+            kind, dt, levels = cpu_bfs_baseline(h_rp, h_ci, source)
+            got = result_vec.extractTuples().astype(np.int32)
+            parity = bool(np.array_equal(got, levels))
+            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
+                            "cores": 1, "kind": kind, "ms": dt * 1e3,
+                            "host_cores_total": os.cpu_count(),
+                            "sample": "one full BFS of the same graph from the "
+                                      "same source"}
+        elif args.algo == "sssp":
+            import oracle_binding as orc
+            kind = "reference" if orc.ref() is not None else "port"
+            fn = orc.ref_sssp if kind == "reference" else orc.sssp
+            t0 = time.perf_counter()
+            dist = fn(h_rp, h_ci, w, source)
+            dt = time.perf_counter() - t0
+            parity = bool(np.array_equal(result_vec.extractTuples(), dist))
+            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
+                            "cores": 1, "kind": kind, "ms": dt * 1e3,
+                            "host_cores_total": os.cpu_count(),
+                            "sample": "one full SSSP of the same graph"}
+
+    out = {
+        "metric": "MTEPS", "value": mteps,
+        "unit": "MTEPS (stored entries of A / traversal time x 1e-6)",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, n, nnz, source),
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches1.value - launches0.value),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "parity_vs_cpu_reference": parity,
+    }
+    if args.algo == "tc":
+        out["triangles"] = int(tc_count[0])
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -843,6 +843,39 @@ int gb200_tc(long long* ntris, gb200_matrix_t A, gb200_matrix_t B,
   return 0;
 }
 
+// ---- Measurement hooks --------------------------------------------------------
+
+int gb200_profile_enable(int on) {
+  GB200_REQUIRE_DEVICE();
+  graphblas::backend::profiler().enabled = (on != 0);
+  if (on) graphblas::backend::profiler().ensureCells();
+  return 0;
+}
+
+int gb200_profile_reset(void) {
+  GB200_REQUIRE_DEVICE();
+  graphblas::backend::profiler().reset(graphblas::backend::gbStream());
+  return 0;
+}
+
+int gb200_profile_read(int kind, double* ms, long long* launches,
+                       double* bytes) {
+  if (ms == NULL || launches == NULL || bytes == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  if (kind < 0 || kind >= GB_PROF_NKINDS)
+    return rc(graphblas::GrB_INVALID_VALUE);
+  GB200_REQUIRE_DEVICE();
+  graphblas::backend::profiler().read(kind, graphblas::backend::gbStream(), ms,
+      launches, bytes);
+  return 0;
+}
+
+int gb200_launch_count(unsigned long long* out) {
+  if (out == NULL) return rc(graphblas::GrB_NULL_POINTER);
+  *out = graphblas::backend::launchCounter();
+  return 0;
+}
+
 // ---- Graph ingest -------------------------------------------------------------
 
 __global__ void rmatEdgesKernel(int scale, long long nedges,
@@ -882,6 +915,7 @@ int gb200_rmat_edges(int scale, long long nedges, unsigned long long seed,
   rmatEdgesKernel<<<grid, 256, 0, graphblas::backend::gbStream()>>>(scale,
       nedges, seed, first_edge, d_src, d_dst);
   if (cudaGetLastError() != cudaSuccess) return rc(graphblas::GrB_PANIC);
+  ++graphblas::backend::launchCounter();
   return 0;
 }
 

@@ -34,8 +34,10 @@ spgemmMaskedKernel(c* __restrict__           C_val,
                    const Index* __restrict__ B_rowind,
                    const b* __restrict__     B_val,
                    Index                     nrows,
-                   unsigned long long*       work_counter) {
+                   unsigned long long*       work_counter,
+                   unsigned long long*       list_bytes) {
   const int lane = threadIdx.x & 31;
+  unsigned long long scanned = 0;   // lane 0: entries of both lists per mask nnz
   while (true) {
     unsigned long long grab = 0;
     if (lane == 0)
@@ -60,6 +62,7 @@ spgemmMaskedKernel(c* __restrict__           C_val,
           const Index b_beg = B_colptr[j];
           const Index b_end = B_colptr[j + 1];
           const Index b_len = b_end - b_beg;
+          scanned += static_cast<unsigned long long>(a_len + b_len);
           if (a_len <= b_len) {
             for (Index p = a_beg + lane; p < a_end; p += 32) {
               const Index key = __ldg(A_colind + p);
@@ -81,6 +84,8 @@ spgemmMaskedKernel(c* __restrict__           C_val,
       }
     }
   }
+  if (lane == 0 && scanned && list_bytes != NULL)
+    atomicAdd(list_bytes, 4ull*scanned);
 }
 
 }  // namespace backend

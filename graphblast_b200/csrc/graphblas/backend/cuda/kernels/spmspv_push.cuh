@@ -51,7 +51,8 @@ spmspvPushKernel(unsigned int* __restrict__ bits,
                  const a* __restrict__      val,
                  W                          identity,
                  MulOp                      mul_op,
-                 AddOp                      add_op) {
+                 AddOp                      add_op,
+                 unsigned long long*        edge_bytes) {
   __shared__ Index s_offs[GB_PUSH_SEG + 1];
   __shared__ Index s_base[GB_PUSH_SEG];
   __shared__ U     s_uval[GB_PUSH_SEG];
@@ -60,6 +61,10 @@ spmspvPushKernel(unsigned int* __restrict__ bits,
   const Index total = offs[nf];
   const long long ntiles = (static_cast<long long>(total) + GB_PUSH_TILE - 1)
                            / GB_PUSH_TILE;
+  // Algorithmic bytes per expanded edge: colind (+ val) (+ mask lookup).
+  if (blockIdx.x == 0 && threadIdx.x == 0 && edge_bytes != NULL)
+    atomicAdd(edge_bytes, static_cast<unsigned long long>(total) *
+        (4ull + (StructOnly ? 0ull : 4ull) + (MaskMode ? 4ull : 0ull)));
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const Index e0 = static_cast<Index>(tile*GB_PUSH_TILE);

@@ -243,11 +243,13 @@ spmvMaskedOrPullKernel(W* __restrict__           w,
                        const Index* __restrict__ rowptr,
                        const Index* __restrict__ colind,
                        const U* __restrict__     u,
-                       unsigned long long*       discovered) {
+                       unsigned long long*       discovered,
+                       unsigned long long*       inspected_bytes) {
   __shared__ int s_red[GB_PULL_NT/32];
   Index row = blockIdx.x*blockDim.x + threadIdx.x;
   const Index stride = gridDim.x*blockDim.x;
   int found_total = 0;
+  int inspected = 0;
   for (; row < nrows; row += stride) {
     bool found = false;
     const M m = mask[row];
@@ -258,6 +260,7 @@ spmvMaskedOrPullKernel(W* __restrict__           w,
       Index end = rowptr[row + 1];
       for (; k < end; ++k) {
         const Index col = __ldg(colind + k);
+        ++inspected;
         bool hit;
         if (UseOpReuse) hit = (__ldg(mask + col) != static_cast<M>(0));
         else            hit = (__ldg(u + col) != identity);
@@ -273,6 +276,10 @@ spmvMaskedOrPullKernel(W* __restrict__           w,
   int total = blockSum<GB_PULL_NT>(found_total, s_red);
   if (threadIdx.x == 0 && total)
     atomicAdd(discovered, static_cast<unsigned long long>(total));
+  // Algorithmic bytes of the inspected colind entries (E_insp).
+  int insp = blockSum<GB_PULL_NT>(inspected, s_red);
+  if (threadIdx.x == 0 && insp && inspected_bytes != NULL)
+    atomicAdd(inspected_bytes, 4ull*static_cast<unsigned long long>(insp));
 }
 
 }  // namespace backend

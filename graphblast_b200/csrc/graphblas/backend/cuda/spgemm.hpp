@@ -61,12 +61,20 @@ Info spgemmMasked(SparseMatrix<c>*       C,
       cudaStream_t s = gbStream();
       CUDA_CALL(cudaMemsetAsync(work, 0, sizeof(unsigned long long), s));
       const int grid = runtime().sm_count*8;
+      unsigned long long* prof_cell = NULL;
+      if (profiler().enabled) {
+        profiler().ensureCells();
+        prof_cell = profiler().d_cells + GB_PROF_SPGEMM;
+      }
+      profiler().begin(GB_PROF_SPGEMM, s);
       spgemmMaskedKernel<<<grid, GB_SPGEMM_NT, 0, s>>>(C->d_csrVal_,
           sparse_mask->d_csrRowPtr_, sparse_mask->d_csrColInd_,
           sparse_mask->d_csrVal_, extractMul(op), extractAdd(op),
           static_cast<c>(op.identity()), A_csrRowPtr, A_csrColInd, A_csrVal,
-          B_cscColPtr, B_cscRowInd, B_cscVal, A_nrows, work);
+          B_cscColPtr, B_cscRowInd, B_cscVal, A_nrows, work, prof_cell);
       GB_KERNEL_CHECK();
+      profiler().end(GB_PROF_SPGEMM, s, 8.0*(A_nrows + 1) +
+          8.0*sparse_mask->nvals_);
     }
   }
   C->need_update_ = true;

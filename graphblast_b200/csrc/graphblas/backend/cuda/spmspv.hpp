@@ -160,7 +160,14 @@ Info spmspvMerge(SparseVector<W>*       w,
 #define GB_LAUNCH_PUSH(SO, MM)                                               \
   spmspvPushKernel<SO, MM><<<grid, GB_PUSH_NT, 0, s>>>(bits, acc, mask_val,  \
       offs, u->d_ind_, u->d_val_, nf, A_csrRowPtr, A_csrColInd, A_csrVal,    \
-      static_cast<W>(op.identity()), extractMul(op), extractAdd(op))
+      static_cast<W>(op.identity()), extractMul(op), extractAdd(op),      \
+      prof_cell)
+  unsigned long long* prof_cell = NULL;
+  if (profiler().enabled) {
+    profiler().ensureCells();
+    prof_cell = profiler().d_cells + GB_PROF_PUSH;
+  }
+  profiler().begin(GB_PROF_PUSH, s);
   if (struconly) {
     if (mask_mode == 0)      GB_LAUNCH_PUSH(true, 0);
     else if (mask_mode == 1) GB_LAUNCH_PUSH(true, 1);
@@ -172,6 +179,7 @@ Info spmspvMerge(SparseVector<W>*       w,
   }
 #undef GB_LAUNCH_PUSH
   GB_KERNEL_CHECK();
+  profiler().end(GB_PROF_PUSH, s, 12.0*nf);   // ind + rowptr pair per frontier entry
 
   // 3) ordered compaction of the touched bitmap -> sorted unique output.
   const Index nwords = (out_size + 31)/32;
@@ -197,6 +205,8 @@ Info spmspvMerge(SparseVector<W>*       w,
   }
   w->nvals_       = count;
   w->need_update_ = true;
+  if (profiler().enabled)
+    profiler().host_bytes[GB_PROF_PUSH] += 8.0*count;   // (ind, val) written
 
   if (desc->debug()) {
     std::cout << "Frontier size: " << w->nvals_ << std::endl;

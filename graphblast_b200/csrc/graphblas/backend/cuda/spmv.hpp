@@ -44,6 +44,8 @@ Info spmvMergeLaunch(W*           out,
       (reinterpret_cast<uintptr_t>(colind) % 32 == 0) &&
       (reinterpret_cast<uintptr_t>(val)    % 32 == 0) &&
       sizeof(a) == 4 && sizeof(Index) == 4;
+  const double alg_bytes = 8.0*nnz + 12.0*nrows + 4.0;
+  profiler().begin(GB_PROF_SPMV_MERGE, s);
   if (aligned)
     spmvMergeKernel<true><<<nctas, GB_SPMV_NT, 0, s>>>(out, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
@@ -56,6 +58,7 @@ Info spmvMergeLaunch(W*           out,
   spmvCarryFixupKernel<<<(nctas + 255)/256, 256, 0, s>>>(out, carry_row,
       carry_val, nctas, extractAdd(op));
   GB_KERNEL_CHECK();
+  profiler().end(GB_PROF_SPMV_MERGE, s, alg_bytes);
   return GrB_SUCCESS;
 }
 
@@ -125,7 +128,13 @@ Info spmv(DenseVector<W>*        w,
 #define GB_LAUNCH_PULL(SC, EE, OR)                                           \
       spmvMaskedOrPullKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(        \
           w->d_val_, mask_val, op.identity(), A_nrows, A_csrRowPtr,          \
-          A_csrColInd, u_t->d_val_, ctr)
+          A_csrColInd, u_t->d_val_, ctr, prof_cell)
+      unsigned long long* prof_cell = NULL;
+      if (profiler().enabled) {
+        profiler().ensureCells();
+        prof_cell = profiler().d_cells + GB_PROF_PULL_BOOL;
+      }
+      profiler().begin(GB_PROF_PULL_BOOL, s);
       switch (variant) {
         case 0: GB_LAUNCH_PULL(false, false, false); break;
         case 1: GB_LAUNCH_PULL(false, false, true ); break;
@@ -139,6 +148,8 @@ Info spmv(DenseVector<W>*        w,
       }
 #undef GB_LAUNCH_PULL
       GB_KERNEL_CHECK();
+      // rowptr + mask + output; the inspected colind bytes are added on device
+      profiler().end(GB_PROF_PULL_BOOL, s, 4.0*(A_nrows + 1) + 8.0*A_nrows);
       w->touched();
       // The kernel wrote 0/1 and counted the ones: the next convert() or
       // a PlusMonoid reduce can reuse the count (one 8-byte read, no pass).

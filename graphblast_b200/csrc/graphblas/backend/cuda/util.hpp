@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <vector>
 
 #define CUDA_SAFE_CALL_NO_SYNC(call) do {                                    \
   cudaError_t gb_err__ = (call);                                             \
@@ -26,11 +27,105 @@
 
 #define CUDA_CALL(call) CUDA_SAFE_CALL_NO_SYNC(call)
 
-// After a kernel launch: catches launch-configuration errors immediately.
-#define GB_KERNEL_CHECK() CUDA_SAFE_CALL_NO_SYNC(cudaGetLastError())
+// After a kernel launch: catches launch-configuration errors immediately and
+// counts the launch (bench.py reports gpu_launches from this counter).
+#define GB_KERNEL_CHECK() do {                                               \
+  CUDA_SAFE_CALL_NO_SYNC(cudaGetLastError());                                \
+  ++graphblas::backend::launchCounter();                                     \
+} while (0)
+
+// Hot-kernel kinds timed by the optional profiler (gb200_profile_*).
+#define GB_PROF_SPMV_MERGE 0
+#define GB_PROF_PULL_BOOL  1
+#define GB_PROF_PUSH       2
+#define GB_PROF_SPGEMM     3
+#define GB_PROF_NKINDS     4
 
 namespace graphblas {
 namespace backend {
+
+inline unsigned long long& launchCounter() {
+  static unsigned long long count = 0;
+  return count;
+}
+
+// ---------------------------------------------------------------------------
+// Optional hot-kernel profiler.  When enabled, every launch of a hot kernel is
+// bracketed by two cudaEvents on the launching stream; reading a kind sums the
+// elapsed times.  Algorithmic bytes that are only known on the device (edges
+// inspected by the early-exit pull, edges expanded by the push) are accumulated
+// by the kernels themselves into d_cells.  Off by default: no events, and the
+// kernels' accumulation is one atomic per CTA.
+// ---------------------------------------------------------------------------
+struct Profiler {
+  bool enabled;
+  std::vector<cudaEvent_t> start[GB_PROF_NKINDS];
+  std::vector<cudaEvent_t> stop[GB_PROF_NKINDS];
+  size_t used[GB_PROF_NKINDS];
+  double host_bytes[GB_PROF_NKINDS];       // algorithmic bytes known on the host
+  unsigned long long* d_cells;             // [kind] device-side byte/edge counters
+
+  Profiler() : enabled(false), d_cells(NULL) {
+    for (int k = 0; k < GB_PROF_NKINDS; ++k) { used[k] = 0; host_bytes[k] = 0; }
+  }
+
+  void ensureCells() {
+    if (d_cells == NULL) {
+      CUDA_CALL(cudaMalloc(&d_cells, GB_PROF_NKINDS*sizeof(unsigned long long)));
+      CUDA_CALL(cudaMemset(d_cells, 0, GB_PROF_NKINDS*sizeof(unsigned long long)));
+    }
+  }
+
+  void begin(int kind, cudaStream_t s) {
+    if (!enabled) return;
+    if (used[kind] == start[kind].size()) {
+      cudaEvent_t a, b;
+      CUDA_CALL(cudaEventCreate(&a));
+      CUDA_CALL(cudaEventCreate(&b));
+      start[kind].push_back(a);
+      stop[kind].push_back(b);
+    }
+    CUDA_CALL(cudaEventRecord(start[kind][used[kind]], s));
+  }
+
+  void end(int kind, cudaStream_t s, double bytes) {
+    if (!enabled) return;
+    CUDA_CALL(cudaEventRecord(stop[kind][used[kind]], s));
+    ++used[kind];
+    host_bytes[kind] += bytes;
+  }
+
+  void reset(cudaStream_t s) {
+    ensureCells();
+    for (int k = 0; k < GB_PROF_NKINDS; ++k) { used[k] = 0; host_bytes[k] = 0; }
+    CUDA_CALL(cudaMemsetAsync(d_cells, 0,
+        GB_PROF_NKINDS*sizeof(unsigned long long), s));
+  }
+
+  // Total milliseconds, launches and bytes of one kind (synchronises).
+  void read(int kind, cudaStream_t s, double* ms, long long* launches,
+            double* bytes) {
+    ensureCells();
+    CUDA_CALL(cudaStreamSynchronize(s));
+    double total = 0;
+    for (size_t i = 0; i < used[kind]; ++i) {
+      float t = 0.f;
+      CUDA_CALL(cudaEventElapsedTime(&t, start[kind][i], stop[kind][i]));
+      total += t;
+    }
+    unsigned long long cell = 0;
+    CUDA_CALL(cudaMemcpy(&cell, d_cells + kind, sizeof(cell),
+        cudaMemcpyDeviceToHost));
+    *ms = total;
+    *launches = static_cast<long long>(used[kind]);
+    *bytes = host_bytes[kind] + static_cast<double>(cell);
+  }
+};
+
+inline Profiler& profiler() {
+  static Profiler p;
+  return p;
+}
 
 // ---------------------------------------------------------------------------
 // Runtime context: one per process (one process per GPU).

@@ -198,6 +198,18 @@ int gb200_pr(gb200_vector_t p, gb200_matrix_t A, float alpha, float eps,
 int gb200_tc(long long* ntris, gb200_matrix_t A, gb200_matrix_t B,
              gb200_desc_t desc, float* tight_ms);               /* algorithm/tc.hpp:15-54 */
 
+/* ---- Measurement hooks (bench.py; no reference counterpart) --------------- */
+/* Hot-kernel kinds: 0 merge-path SpMV (pull, generic semiring), 1 fused Boolean
+ * pull, 2 push (SpMSpV expand), 3 masked SpGEMM.  When enabled every launch of
+ * those kernels is bracketed by CUDA events on the launching stream. */
+int gb200_profile_enable(int on);
+int gb200_profile_reset(void);
+/* Sum over the launches since the last reset: device milliseconds, launch count
+ * and ALGORITHMIC bytes (SURVEY.md §8d definitions). */
+int gb200_profile_read(int kind, double* ms, long long* launches, double* bytes);
+/* Number of kernels this library has launched so far. */
+int gb200_launch_count(unsigned long long* out);
+
 /* ---- Graph ingest helpers (ours, no reference counterpart) */
 /* R-MAT (0.57,0.19,0.19,0.05) edges [first_edge, first_edge+nedges) into DEVICE
  * arrays; bit-identical to oracle/gb_oracle.c:orc_rmat_edges. */

@@ -1,0 +1,57 @@
+"""The UNCHANGED reference drivers (example/gbfs.cu, gsssp.cu, gpr.cu, gtc.cu),
+compiled against this backend into build/dropin/ where the reference sources are
+mounted, run on the bundled graph and must print CORRECT for every self-check
+(each driver compares against the reference's own CPU implementation,
+test/test.hpp:60-122)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "build", "dropin")
+
+
+def run_driver(name, flags, tmp_path):
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        pytest.skip("build/dropin/%s not built (needs /root/reference at build time)" % name)
+    # the drivers write a .bin cache next to the .mtx: work on a copy
+    mtx = os.path.join(str(tmp_path), "chesapeake.mtx")
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "chesapeake.mtx"), mtx)
+    out = subprocess.run([exe] + flags + [mtx], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:]
+    return out.stdout
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_gbfs_unchanged(mode, tmp_path):
+    out = run_driver("gbfs", ["--mxvmode", mode, "--struconly", "1", "--opreuse",
+                              "1", "--earlyexit", "1", "--niter", "2",
+                              "--timing", "0", "--directed", "2"], tmp_path)
+    assert out.count("\nCORRECT") == 2 and "INCORRECT" not in out
+    assert "Search depth is: 3" in out
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_gsssp_unchanged(mode, tmp_path):
+    out = run_driver("gsssp", ["--mxvmode", mode, "--niter", "2", "--timing", "0",
+                               "--directed", "2", "--seed", "1"], tmp_path)
+    assert out.count("\nCORRECT") == 2 and "INCORRECT" not in out
+
+
+def test_gpr_unchanged(tmp_path):
+    out = run_driver("gpr", ["--mxvmode", "0", "--niter", "2", "--max_niter",
+                             "10", "--timing", "0", "--directed", "2"], tmp_path)
+    assert out.count("\nCORRECT") == 2 and "INCORRECT" not in out
+
+
+def test_gtc_unchanged(tmp_path):
+    out = run_driver("gtc", ["--mxvmode", "0", "--niter", "1", "--timing", "0",
+                             "--directed", "2"], tmp_path)
+    assert out.count("\nCORRECT") == 2 and "INCORRECT" not in out
+    assert "Number of triangles: 194" in out
