@@ -50,63 +50,70 @@ def parse_args():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,"
-             "clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML
+    (a polling thread; nvidia-smi's own loop is too slow for millisecond regions).
+    Falls back to one nvidia-smi query when pynvml is unavailable."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self.stop_flag = False
         self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index),
-                 "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(
+                self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nvml = None
             return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread = threading.Thread(target=self._poll, daemon=True)
         self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self.nvml
+        names = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")]
+        masks = [(n, getattr(nv, a, 0)) for n, a in names]
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(
+                    self.handle, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for n, m in masks:
+                    if m and (r & m):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.0005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                 "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
+        if self.nvml is None:
             try:
-                sm.append(float(parts[0]))
-                smax = float(parts[1])
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": smax, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                q = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index),
+                     "--query-gpu=clocks.sm,clocks.max.sm",
+                     "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                    text=True, timeout=20).stdout.split(",")
+                return {"sm_mhz": float(q[0]), "sm_max_mhz": float(q[1]),
+                        "samples": 1, "reasons": ["sampled after the region"]}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0,
+                        "reasons": ["unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.sm_max, "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
 
 
 def measured_peak_hbm():

@@ -843,6 +843,73 @@ int gb200_tc(long long* ntris, gb200_matrix_t A, gb200_matrix_t B,
   return 0;
 }
 
+// ---- Frontier exchange helpers --------------------------------------------------
+
+int gb200_vector_export_bits(gb200_vector_t v, uint32_t* d_bits,
+                             long long* count_out) {
+  if (v == NULL || d_bits == NULL) return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  using namespace graphblas::backend;
+  Vector<float>& b = v->f->vector_;
+  cudaStream_t s = gbStream();
+  const size_t nwords = (static_cast<size_t>(b.nsize_) + 31)/32;
+  if (b.vec_type_ == graphblas::GrB_DENSE) {
+    const unsigned int* bits = b.dense_.ensureBits();
+    CUDA_CALL(cudaMemcpyAsync(d_bits, bits, nwords*sizeof(unsigned int),
+        cudaMemcpyDeviceToDevice, s));
+  } else if (b.vec_type_ == graphblas::GrB_SPARSE) {
+    CUDA_CALL(cudaMemsetAsync(d_bits, 0, nwords*sizeof(unsigned int), s));
+    if (b.sparse_.nvals_ > 0) {
+      scatterBitsKernel<<<gridFor(b.sparse_.nvals_, 256), 256, 0, s>>>(d_bits,
+          b.sparse_.d_ind_, b.sparse_.nvals_);
+      GB_KERNEL_CHECK();
+    }
+  } else {
+    return rc(graphblas::GrB_UNINITIALIZED_OBJECT);
+  }
+  if (count_out != NULL) {
+    if (b.vec_type_ == graphblas::GrB_SPARSE) {
+      *count_out = b.sparse_.nvals_;
+    } else {
+      static unsigned long long* cell = NULL;
+      if (cell == NULL) CUDA_CALL(cudaMalloc(&cell, sizeof(unsigned long long)));
+      CUDA_CALL(cudaMemsetAsync(cell, 0, sizeof(unsigned long long), s));
+      popcountKernel<<<gridFor(nwords, 256), 256, 0, s>>>(cell, d_bits,
+          static_cast<graphblas::Index>(nwords));
+      GB_KERNEL_CHECK();
+      *count_out = static_cast<long long>(runtime().fetch(cell));
+    }
+  }
+  return 0;
+}
+
+int gb200_vector_import_bits(gb200_vector_t v, const uint32_t* d_bits,
+                             long long nnz) {
+  if (v == NULL || d_bits == NULL) return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  using namespace graphblas::backend;
+  Vector<float>& b = v->f->vector_;
+  cudaStream_t s = gbStream();
+  Info info = b.setStorage(graphblas::GrB_DENSE);
+  if (info != GrB_SUCCESS) return rc(info);
+  DenseVector<float>& d = b.dense_;
+  const graphblas::Index n = d.nvals_;
+  unsigned int* bits = d.bitsStorage();
+  CUDA_CALL(cudaMemcpyAsync(bits, d_bits, d.bitWords()*sizeof(unsigned int),
+      cudaMemcpyDeviceToDevice, s));
+  bitmapToDenseKernel<<<gridFor(n, 256), 256, 0, s>>>(d.d_val_, bits, n);
+  GB_KERNEL_CHECK();
+  d.touched();
+  d.bits_valid_ = true;
+  d.zero_one_   = true;
+  if (nnz >= 0) {
+    d.nnz_          = static_cast<graphblas::Index>(nnz);
+    d.nnz_valid_    = true;
+    d.nnz_identity_ = 0.f;
+  }
+  return 0;
+}
+
 // ---- Measurement hooks --------------------------------------------------------
 
 int gb200_profile_enable(int on) {

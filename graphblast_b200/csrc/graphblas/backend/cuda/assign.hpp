@@ -56,29 +56,53 @@ Info assignDense(DenseVector<W>*  w,
   Storage mask_vec_type;
   CHECK(mask->getStorage(&mask_vec_type));
 
+  // The target's bitmap shadow survives a constant assign when the mask's
+  // selection is available as bits (dense mask with a valid shadow, or a sparse
+  // mask): exactly the assign(v<f> = level) of the BFS loop.
+  bool bits_kept = false;
   if (mask_vec_type == GrB_DENSE) {
     const int grid = gridFor(w->nvals_, 256);
-    if (use_scmp)
+    if (mask->dense_.bits_valid_) {
+      unsigned int* w_bits = w->bits_valid_ ? w->d_bits_ : NULL;
+      if (use_scmp)
+        assignDenseBitsMaskKernel<true><<<grid, 256, 0, s>>>(w->d_val_, w_bits,
+            w->nvals_, mask->dense_.d_bits_, static_cast<W>(val));
+      else
+        assignDenseBitsMaskKernel<false><<<grid, 256, 0, s>>>(w->d_val_, w_bits,
+            w->nvals_, mask->dense_.d_bits_, static_cast<W>(val));
+      bits_kept = (w_bits != NULL);
+    } else if (use_scmp) {
       assignDenseDenseMaskKernel<true><<<grid, 256, 0, s>>>(w->d_val_,
           w->nvals_, mask->dense_.d_val_, static_cast<W>(val));
-    else
+    } else {
       assignDenseDenseMaskKernel<false><<<grid, 256, 0, s>>>(w->d_val_,
           w->nvals_, mask->dense_.d_val_, static_cast<W>(val));
+    }
     GB_KERNEL_CHECK();
   } else if (mask_vec_type == GrB_SPARSE) {
     if (use_scmp) {
       std::cout << "All Indices DeVec Assign Constant Scmp Kernel\n";
       std::cout << "Error: Feature not implemented yet!\n";
     } else if (mask->sparse_.nvals_ > 0) {
-      assignDenseSparseMaskKernel<<<gridFor(mask->sparse_.nvals_, 256), 256, 0,
-          s>>>(w->d_val_, mask->sparse_.d_ind_, mask->sparse_.nvals_,
-          static_cast<W>(val));
+      const int grid = gridFor(mask->sparse_.nvals_, 256);
+      if (w->bits_valid_) {
+        assignDenseSparseMaskBitsKernel<<<grid, 256, 0, s>>>(w->d_val_,
+            w->d_bits_, mask->sparse_.d_ind_, mask->sparse_.nvals_,
+            static_cast<W>(val));
+        bits_kept = true;
+      } else {
+        assignDenseSparseMaskKernel<<<grid, 256, 0, s>>>(w->d_val_,
+            mask->sparse_.d_ind_, mask->sparse_.nvals_, static_cast<W>(val));
+      }
       GB_KERNEL_CHECK();
+    } else {
+      bits_kept = w->bits_valid_;
     }
   } else {
     return GrB_UNINITIALIZED_OBJECT;
   }
   w->touched();
+  w->bits_valid_ = bits_kept;
   return GrB_SUCCESS;
 }
 

@@ -35,12 +35,14 @@ class DenseVector {
   DenseVector()
       : nvals_(0), nnz_(0), h_val_(NULL), d_val_(NULL), need_update_(0),
         owns_device_(true), nnz_valid_(false), nnz_identity_(T()),
-        d_count_(NULL), count_pending_(false), zero_one_(false) {}
+        d_count_(NULL), count_pending_(false), zero_one_(false),
+        d_bits_(NULL), bits_valid_(false), bits_alloc_words_(0) {}
 
   explicit DenseVector(Index nsize)
       : nvals_(nsize), nnz_(0), h_val_(NULL), d_val_(NULL), need_update_(0),
         owns_device_(true), nnz_valid_(false), nnz_identity_(T()),
-        d_count_(NULL), count_pending_(false), zero_one_(false) {}
+        d_count_(NULL), count_pending_(false), zero_one_(false),
+        d_bits_(NULL), bits_valid_(false), bits_alloc_words_(0) {}
 
   ~DenseVector();
 
@@ -91,6 +93,7 @@ class DenseVector {
     nnz_valid_ = false;
     count_pending_ = false;
     zero_one_ = false;
+    bits_valid_ = false;
   }
 
  public:  // (private in the reference; its drivers `#define private public`)
@@ -110,6 +113,36 @@ class DenseVector {
   bool  count_pending_;
   bool  zero_one_;     // contents are exactly 0/1 (so a plus-reduce == count)
 
+  // Bitmap shadow: bit i == (d_val_[i] != 0).  Kept by the operations of the
+  // BFS loop (fill, fused Boolean pull, masked constant assign); any other write
+  // invalidates it.  Lets masks and Boolean frontiers be read at 1 bit/vertex.
+  unsigned int* d_bits_;
+  bool  bits_valid_;
+  size_t bits_alloc_words_;
+
+  size_t bitWords() const { return (static_cast<size_t>(nvals_) + 31)/32; }
+  unsigned int* bitsStorage() {
+    if (d_bits_ == NULL || bits_alloc_words_ < bitWords()) {
+      if (d_bits_ != NULL) gbFree(d_bits_);
+      bits_alloc_words_ = bitWords() + 8;
+      d_bits_ = reinterpret_cast<unsigned int*>(
+          gbMalloc(bits_alloc_words_*sizeof(unsigned int)));
+      bits_valid_ = false;
+    }
+    return d_bits_;
+  }
+  // Returns a valid bitmap of the current contents, building it if needed.
+  unsigned int* ensureBits() {
+    unsigned int* b = bitsStorage();
+    if (!bits_valid_) {
+      denseToBitmapKernel<<<gridFor(static_cast<size_t>(nvals_), 256), 256, 0,
+          gbStream()>>>(b, d_val_, nvals_);
+      GB_KERNEL_CHECK();
+      bits_valid_ = true;
+    }
+    return b;
+  }
+
   unsigned long long* countCell() {
     if (d_count_ == NULL)
       d_count_ = reinterpret_cast<unsigned long long*>(
@@ -123,6 +156,7 @@ DenseVector<T>::~DenseVector() {
   if (h_val_ != NULL) free(h_val_);
   if (d_val_ != NULL && owns_device_) gbFree(d_val_);
   if (d_count_ != NULL) gbFree(d_count_);
+  if (d_bits_ != NULL) gbFree(d_bits_);
 }
 
 template <typename T>
@@ -132,11 +166,14 @@ Info DenseVector<T>::nnew(Index nsize) {
     if (d_val_ != NULL && owns_device_) gbFree(d_val_);
     d_val_ = NULL;
     owns_device_ = true;
+    if (d_bits_ != NULL) gbFree(d_bits_);
+    d_bits_ = NULL;
   }
   nvals_ = nsize;
   nnz_valid_ = false;
   count_pending_ = false;
   zero_one_ = false;
+  bits_valid_ = false;
   return GrB_SUCCESS;
 }
 
@@ -242,6 +279,7 @@ Info DenseVector<T>::build(T*    values,
   nnz_valid_   = false;
   count_pending_ = false;
   zero_one_ = false;
+  bits_valid_ = false;
   return GrB_SUCCESS;
 }
 
@@ -259,6 +297,7 @@ Info DenseVector<T>::setElement(T val, Index index) {
   nnz_valid_ = false;
   count_pending_ = false;
   zero_one_ = false;
+  bits_valid_ = false;
   return GrB_SUCCESS;
 }
 
@@ -340,6 +379,7 @@ Info DenseVector<T>::resize(Index nsize) {
   nnz_valid_ = false;
   count_pending_ = false;
   zero_one_ = false;
+  bits_valid_ = false;
   return GrB_SUCCESS;
 }
 
@@ -354,6 +394,10 @@ Info DenseVector<T>::fill(T val) {
   nnz_valid_   = false;
   count_pending_ = false;
   zero_one_ = false;
+  // bitmap shadow of a constant vector: all zero or all one
+  CUDA_CALL(cudaMemsetAsync(bitsStorage(), (val != static_cast<T>(0)) ? 0xff : 0,
+      bitWords()*sizeof(unsigned int), gbStream()));
+  bits_valid_ = true;
   return GrB_SUCCESS;
 }
 
@@ -367,6 +411,7 @@ Info DenseVector<T>::fillAscending(Index nvals) {
   nnz_valid_   = false;
   count_pending_ = false;
   zero_one_ = false;
+  bits_valid_ = false;
   return GrB_SUCCESS;
 }
 
@@ -426,6 +471,7 @@ Info DenseVector<T>::cpuToGpu() {
   nnz_valid_   = false;
   count_pending_ = false;
   zero_one_ = false;
+  bits_valid_ = false;
   return GrB_SUCCESS;
 }
 
@@ -456,6 +502,9 @@ Info DenseVector<T>::swap(DenseVector* rhs) {  // NOLINT(build/include_what_you_
   std::swap(d_count_,      rhs->d_count_);
   std::swap(count_pending_, rhs->count_pending_);
   std::swap(zero_one_,     rhs->zero_one_);
+  std::swap(d_bits_,       rhs->d_bits_);
+  std::swap(bits_valid_,   rhs->bits_valid_);
+  std::swap(bits_alloc_words_, rhs->bits_alloc_words_);
   return GrB_SUCCESS;
 }
 }  // namespace backend

@@ -193,6 +193,28 @@ __device__ __forceinline__ int upperBound(const int* a, int n, int key) {
   return lo;
 }
 
+// upper_bound executed by a whole warp as a 32-ary search: every step probes 32
+// evenly spaced positions at once, so a search over n elements costs
+// ceil(log32 n) dependent loads instead of log2 n.  All 32 lanes must call it
+// with the same arguments; all lanes return the result.
+__device__ __forceinline__ int warpUpperBound(const int* a, int n, int key) {
+  const int lane = threadIdx.x & 31;
+  int lo = 0, hi = n;
+  while (hi > lo) {
+    const int step = (hi - lo + 31) >> 5;
+    const int idx  = lo + lane*step;
+    const bool gt  = (idx < hi) ? (__ldg(a + idx) > key) : true;
+    const unsigned m = __ballot_sync(GB_FULL_MASK, gt);
+    const int first = m ? (__ffs(m) - 1) : 32;
+    const int cand   = lo + first*step;
+    const int new_hi = (first == 0) ? lo : (cand < hi ? cand : hi);
+    const int new_lo = (first == 0) ? lo : lo + (first - 1)*step + 1;
+    lo = new_lo;
+    hi = new_hi;
+  }
+  return lo;
+}
+
 // Exact-match binary search in a sorted int array segment [lo, hi); -1 if absent.
 __device__ __forceinline__ int findSorted(const int* a, int lo, int hi, int key) {
   while (lo < hi) {

@@ -166,6 +166,30 @@ struct BitmapCompactSource {
   }
 };
 
+// Bitmap shadow of a dense vector (bit == value != 0) -> sparse (ind, val) for
+// identity 0.  Read-only: one item = one word.
+template <typename T, bool StructOnly>
+struct DenseBitsCompactSource {
+  const unsigned int* bits;
+  const T*            u;
+  Index*              out_ind;
+  T*                  out_val;
+
+  __device__ int count(Index item) const { return __popc(bits[item]); }
+  __device__ void emit(Index item, Index pos) const {
+    unsigned int word = bits[item];
+    while (word) {
+      const int b = __ffs(word) - 1;
+      word &= word - 1;
+      const Index idx = item*32 + b;
+      out_ind[pos] = idx;
+      if (!StructOnly) out_val[pos] = u[idx];
+      ++pos;
+    }
+  }
+  __device__ void finish(Index) const {}
+};
+
 // Sparse vector filter: drop entries that the masked constant-assign would have
 // overwritten with `val`, and entries already equal to `val`
 // (reference assign.hpp:172-221: assignSparseKernel marks, updateFlag/scan/

@@ -200,6 +200,58 @@ __global__ void assignDenseDenseMaskKernel(U* u, Index n, const M* mask,
   }
 }
 
+// Masked constant assign, dense target, dense mask given as its bitmap shadow.
+// One lane per row, one mask word per warp (broadcast load); optionally keeps
+// the target's own bitmap shadow exact (val != 0 sets the selected bits, val == 0
+// clears them).
+template <bool UseScmp, typename U>
+__global__ void assignDenseBitsMaskKernel(U* u, unsigned int* u_bits, Index n,
+                                          const unsigned int* mask_bits,
+                                          U val) {
+  const int lane = threadIdx.x & 31;
+  Index word = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+  const Index nwarps = (gridDim.x*blockDim.x) >> 5;
+  const Index nwords = (n + 31) >> 5;
+  for (; word < nwords; word += nwarps) {
+    unsigned int sel = __ldg(mask_bits + word);
+    if (UseScmp) sel = ~sel;
+    const Index base = word*32;
+    if (base + 32 > n) sel &= (n - base >= 32) ? 0xffffffffu
+                                                : ((1u << (n - base)) - 1u);
+    if (sel == 0u) continue;
+    if ((sel >> lane) & 1u) u[base + lane] = val;
+    if (u_bits != NULL && lane == 0) {
+      if (val != static_cast<U>(0)) u_bits[word] |= sel;
+      else                          u_bits[word] &= ~sel;
+    }
+  }
+}
+
+// Masked constant assign, dense target, sparse mask, keeping the bitmap shadow.
+template <typename U>
+__global__ void assignDenseSparseMaskBitsKernel(U* u, unsigned int* u_bits,
+                                                const Index* mask_ind,
+                                                Index mask_nvals, U val) {
+  Index k = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  for (; k < mask_nvals; k += stride) {
+    const Index ind = mask_ind[k];
+    u[ind] = val;
+    const unsigned int m = 1u << (ind & 31);
+    if (val != static_cast<U>(0)) atomicOr(u_bits + (ind >> 5), m);
+    else                          atomicAnd(u_bits + (ind >> 5), ~m);
+  }
+}
+
+// bits[ind[k]] = 1 (bitmap shadow of a scatter of non-zero constants)
+__global__ void scatterBitsKernel(unsigned int* bits, const Index* ind,
+                                  Index nvals) {
+  Index k = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  for (; k < nvals; k += stride)
+    atomicOr(bits + (ind[k] >> 5), 1u << (ind[k] & 31));
+}
+
 // Masked constant assign, dense target, sparse mask (non-complemented only:
 // the reference's SCMP variant is "not implemented", assign_dense.hpp:58-63).
 template <typename U>

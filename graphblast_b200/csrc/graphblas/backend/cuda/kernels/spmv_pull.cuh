@@ -25,7 +25,7 @@
 namespace graphblas {
 namespace backend {
 
-#define GB_SPMV_NT   256
+#define GB_SPMV_NT   128
 #define GB_SPMV_IPT  7                               // merge items per thread
 #define GB_SPMV_TILE (GB_SPMV_NT*GB_SPMV_IPT)        // merge items per CTA
 
@@ -48,10 +48,28 @@ __device__ __forceinline__ Index mergePathRows(long long d,
   return static_cast<Index>(lo);
 }
 
-template <bool Vec256, typename W, typename a, typename U,
+// tile_rows[c] = rows consumed at the start of tile c, for c in [0, ntiles].
+// Every search is an independent chain of ~log2(n) dependent loads; doing them
+// all in parallel here (and caching the result per matrix, the partition only
+// depends on rowptr) takes that latency chain out of every SpMV tile.
+__global__ void spmvMergePartitionKernel(Index* __restrict__ tile_rows,
+                                         const Index* __restrict__ rowptr,
+                                         Index nrows, Index nnz, int ntiles,
+                                         int tile_items) {
+  int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c > ntiles) return;
+  const long long total = static_cast<long long>(nrows) + nnz;
+  long long d = static_cast<long long>(c)*tile_items;
+  if (d > total) d = total;
+  tile_rows[c] = mergePathRows(d, rowptr, nrows, nnz);
+}
+
+template <int NT, int IPT, bool Vec256, bool Gather,
+          typename W, typename a, typename U,
           typename MulOp, typename AddOp>
-__global__ void __launch_bounds__(GB_SPMV_NT)
-spmvMergeKernel(W* __restrict__           w,
+__global__ void __launch_bounds__(NT)
+spmvMergeKernelT(W* __restrict__           w,
+                const Index* __restrict__ tile_rows,
                 Index* __restrict__       carry_row,
                 W* __restrict__           carry_val,
                 const Index* __restrict__ rowptr,
@@ -63,108 +81,122 @@ spmvMergeKernel(W* __restrict__           w,
                 W                         identity,
                 MulOp                     mul_op,
                 AddOp                     add_op) {
-  __shared__ Index s_rowend[GB_SPMV_TILE + 1];
-  __shared__ __align__(32) W s_prod[GB_SPMV_TILE + 16];
-  __shared__ W     s_out[GB_SPMV_TILE];
-  __shared__ Index s_wkey[GB_SPMV_NT/32];
-  __shared__ W     s_wval[GB_SPMV_NT/32];
-  __shared__ Index s_split[2];
+  __shared__ Index s_rowend[(NT*IPT) + 1];
+  __shared__ __align__(32) W s_prod[(NT*IPT) + 16];
+  __shared__ W     s_out[(NT*IPT)];
+  __shared__ Index s_start[NT + 1];   // first row-end owned by thread t
+  __shared__ Index s_wkey[NT/32];
+  __shared__ W     s_wval[NT/32];
 
   const int t    = threadIdx.x;
   const int lane = t & 31;
   const int wid  = t >> 5;
 
   const long long total = static_cast<long long>(nrows) + nnz;
-  const long long d0 = static_cast<long long>(blockIdx.x)*GB_SPMV_TILE;
-  long long d1 = d0 + GB_SPMV_TILE; if (d1 > total) d1 = total;
+  const long long d0 = static_cast<long long>(blockIdx.x)*(NT*IPT);
+  long long d1 = d0 + (NT*IPT); if (d1 > total) d1 = total;
+  const int tile_items = static_cast<int>(d1 - d0);
 
-  if (t == 0)  s_split[0] = mergePathRows(d0, rowptr, nrows, nnz);
-  if (t == 32) s_split[1] = mergePathRows(d1, rowptr, nrows, nnz);
-  __syncthreads();
-  const Index r0 = s_split[0];
-  const Index r1 = s_split[1];
+  const Index r0 = __ldg(tile_rows + blockIdx.x);
+  const Index r1 = __ldg(tile_rows + blockIdx.x + 1);
   const Index k0 = static_cast<Index>(d0 - r0);
   const Index k1 = static_cast<Index>(d1 - r1);
   const int   nr = r1 - r0;          // rows that END in this tile
   const int   nk = k1 - k0;          // nonzeros consumed in this tile
   const Index k0a = k0 & ~7;         // 32-byte aligned load window start
 
-  // Row-end offsets for rows r0 .. r1 (the last one is the still-open row).
-  for (int i = t; i <= nr; i += GB_SPMV_NT) {
-    Index r = r0 + i;
-    s_rowend[i] = (r < nrows) ? __ldg(rowptr + r + 1) : nnz;
-  }
-
-  // Products mul(A(k), u[col(k)]) for k in [k0, k1) into s_prod[k - k0a].
+  // ---- phase 1a: issue the streaming loads + gathers of this thread's chunks --
+  // Products mul(A(k), u[col(k)]) for k in [k0, k1) go to s_prod[k - k0a].
   const uint64_t pol = makeEvictLastPolicy();
-  if (nk > 0) {
-    const int nchunks = (k1 - k0a + 7) >> 3;
-    for (int c = t; c < nchunks; c += GB_SPMV_NT) {
-      const Index kb = k0a + (c << 3);
-      Index cols[8];
-      W     prods[8];
-      if (Vec256 && kb + 8 <= nnz) {
-        Word8 cw = ldStream256(colind + kb);
+  const int nchunks = (nk > 0) ? ((k1 - k0a + 7) >> 3) : 0;
+  for (int c = t; c < nchunks; c += NT) {
+    const Index kb = k0a + (c << 3);
+    W prods[8];
+    if (Vec256 && kb + 8 <= nnz) {
+      const Word8 cw = ldStream256(colind + kb);
+      const Word8 vw = ldStream256(val + kb);
+      U uv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cols[j] = cw.w[j];
-        U uv[8];
+      for (int j = 0; j < 8; ++j)
+        uv[j] = Gather ? ldGather(u + cw.w[j], pol)
+                       : static_cast<U>(cw.w[j] & 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) uv[j] = ldGather(u + cols[j], pol);
-        Word8 vw = ldStream256(val + kb);
+      for (int j = 0; j < 8; ++j) {
+        a av;
+        memcpy(&av, &vw.w[j], 4);
+        prods[j] = mul_op(av, uv[j]);
+      }
+    } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a av;
-          memcpy(&av, &vw.w[j], 4);
-          prods[j] = mul_op(av, uv[j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          Index k = kb + j;
-          if (k >= k0 && k < k1) {
-            Index col = ldStream(colind + k);
-            a av = ldStream(val + k);
-            prods[j] = mul_op(av, ldGather(u + col, pol));
-          } else {
-            prods[j] = identity;
-          }
+      for (int j = 0; j < 8; ++j) {
+        const Index k = kb + j;
+        if (k >= k0 && k < k1) {
+          const Index col = ldStream(colind + k);
+          const a av = ldStream(val + k);
+          prods[j] = mul_op(av, ldGather(u + col, pol));
+        } else {
+          prods[j] = identity;
         }
       }
+    }
+    if (sizeof(W) == 4) {
+      float4 lo4, hi4;
+      memcpy(&lo4, &prods[0], 16);
+      memcpy(&hi4, &prods[4], 16);
+      *reinterpret_cast<float4*>(&s_prod[(c << 3)])     = lo4;
+      *reinterpret_cast<float4*>(&s_prod[(c << 3) + 4]) = hi4;
+    } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) s_prod[(c << 3) + j] = prods[j];
     }
   }
+
+  // ---- phase 1b: row-end offsets for rows r0 .. r1 (last = still-open row) ----
+  for (int i = t; i <= nr; i += NT) {
+    const Index r = r0 + i;
+    s_rowend[i] = (r < nrows) ? __ldg(rowptr + r + 1) : nnz;
+  }
   __syncthreads();
 
-  // Thread-level merge path inside the tile.
-  int ld = t*GB_SPMV_IPT;
-  const int tile_items = static_cast<int>(d1 - d0);
-  if (ld > tile_items) ld = tile_items;
-  int lo = ld - nk; if (lo < 0) lo = 0;
-  int hi = ld < nr ? ld : nr;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (s_rowend[mid] <= k0 + (ld - mid - 1)) lo = mid + 1; else hi = mid;
+  // ---- phase 2: thread partition without searching -----------------------------
+  // Row-end i is merge item p_i = i + (rowend_i - k0).  Thread t owns items
+  // [t*IPT, (t+1)*IPT); s_start[t] = #{i : p_i < t*IPT}.  p is increasing, so row
+  // i fills s_start for the owners between its predecessor's owner and its own.
+  for (int i = t; i <= nr; i += NT) {
+    const int own  = (i < nr)
+        ? (i + (s_rowend[i] - k0)) / IPT : NT;
+    const int prev = (i > 0)
+        ? (i - 1 + (s_rowend[i - 1] - k0)) / IPT : -1;
+    for (int o = prev + 1; o <= own; ++o) s_start[o] = i;
   }
-  int   i = lo;                       // local row
-  Index k = k0 + (ld - lo);           // global nonzero index
+  __syncthreads();
+
+  // ---- phase 3: sequential merge of this thread's IPT items ----------------------
+  int ld = t*IPT;
+  if (ld > tile_items) ld = tile_items;
+  int nit = tile_items - ld;
+  if (nit > IPT) nit = IPT;
+  int   i = s_start[t];               // local row
+  Index k = k0 + (ld - i);            // global nonzero index
   const int first_i = i;
   W acc = identity;
+  Index rowend = s_rowend[i];
 #pragma unroll
-  for (int it = 0; it < GB_SPMV_IPT; ++it) {
-    if (ld + it < tile_items) {
-      if (k < s_rowend[i]) {
+  for (int it = 0; it < IPT; ++it) {
+    if (it < nit) {
+      if (k < rowend) {
         acc = add_op(acc, s_prod[k - k0a]);
         ++k;
       } else {
         s_out[i] = acc;
         acc = identity;
         ++i;
+        rowend = s_rowend[i];
       }
     }
   }
 
-  // Segmented inclusive scan of (key = open row, value = partial) over the CTA.
+  // ---- phase 4: segmented scan of (open row, partial) over the CTA ----------------
   Index key = i;
   W     v   = acc;
 #pragma unroll
@@ -175,17 +207,20 @@ spmvMergeKernel(W* __restrict__           w,
   }
   if (lane == 31) { s_wkey[wid] = key; s_wval[wid] = v; }
   const Index key0 = __shfl_sync(GB_FULL_MASK, key, 0);
-  Index ekey = __shfl_up_sync(GB_FULL_MASK, key, 1);
-  W     eval = __shfl_up_sync(GB_FULL_MASK, v, 1);
+  const Index ekey = __shfl_up_sync(GB_FULL_MASK, key, 1);
+  const W     eval = __shfl_up_sync(GB_FULL_MASK, v, 1);
   __syncthreads();
   // Fold the tails of the preceding warps.
   Index ck = -1;
   W     cv = identity;
-  for (int ww = 0; ww < wid; ++ww) {
-    Index wk = s_wkey[ww];
-    W     wv = s_wval[ww];
-    if (wk == ck) cv = add_op(cv, wv);
-    else { ck = wk; cv = wv; }
+#pragma unroll
+  for (int ww = 0; ww < NT/32 - 1; ++ww) {
+    if (ww < wid) {
+      const Index wk = s_wkey[ww];
+      const W     wv = s_wval[ww];
+      if (wk == ck) cv = add_op(cv, wv);
+      else { ck = wk; cv = wv; }
+    }
   }
   W carry_in;
   if (lane == 0) {
@@ -194,18 +229,17 @@ spmvMergeKernel(W* __restrict__           w,
     carry_in = eval;                                 // ekey == first_i always
     if (ekey == key0 && ck == ekey) carry_in = add_op(cv, eval);
   }
-  (void)ekey;
 
   if (i > first_i) s_out[first_i] = add_op(carry_in, s_out[first_i]);
 
-  if (t == GB_SPMV_NT - 1) {
+  if (t == NT - 1) {
     W out = (i > first_i) ? acc : add_op(carry_in, acc);
     carry_row[blockIdx.x] = (r0 + i < nrows) ? (r0 + i) : -1;
     carry_val[blockIdx.x] = out;
   }
   __syncthreads();
 
-  for (int j = t; j < nr; j += GB_SPMV_NT) w[r0 + j] = s_out[j];
+  for (int j = t; j < nr; j += NT) w[r0 + j] = s_out[j];
 }
 
 // One thread per CTA carry: the first carry of a run of equal rows folds the
@@ -277,6 +311,65 @@ spmvMaskedOrPullKernel(W* __restrict__           w,
   if (threadIdx.x == 0 && total)
     atomicAdd(discovered, static_cast<unsigned long long>(total));
   // Algorithmic bytes of the inspected colind entries (E_insp).
+  int insp = blockSum<GB_PULL_NT>(inspected, s_red);
+  if (threadIdx.x == 0 && insp && inspected_bytes != NULL)
+    atomicAdd(inspected_bytes, 4ull*static_cast<unsigned long long>(insp));
+}
+
+// ---------------------------------------------------------------------------
+// Bitmap form of the fused masked Boolean pull (the one the BFS loop runs).
+// mask_bits / u_bits hold one bit per vertex (bit == value != 0), so the visited
+// test of a row is a broadcast word load and the neighbour test is a gather into
+// an n/8-byte array (2 MB at RMAT-24) that lives in L1/L2 instead of a 4n-byte
+// float array.  A warp owns 32 consecutive rows = one output word: the new
+// frontier is written both as 0/1 floats (the vector's storage) and, through one
+// ballot, as its bitmap shadow.
+// ---------------------------------------------------------------------------
+template <bool UseScmp, bool UseEarlyExit, bool UseOpReuse, typename W>
+__global__ void __launch_bounds__(GB_PULL_NT)
+spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
+                           unsigned int* __restrict__       w_bits,
+                           const unsigned int* __restrict__ mask_bits,
+                           const unsigned int* __restrict__ u_bits,
+                           Index                            nrows,
+                           const Index* __restrict__        rowptr,
+                           const Index* __restrict__        colind,
+                           unsigned long long*              discovered,
+                           unsigned long long*              inspected_bytes) {
+  __shared__ int s_red[GB_PULL_NT/32];
+  const int lane = threadIdx.x & 31;
+  Index word = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+  const Index nwarps = (gridDim.x*blockDim.x) >> 5;
+  const Index nwords = (nrows + 31) >> 5;
+  const unsigned int* probe = UseOpReuse ? mask_bits : u_bits;
+  int found_total = 0;
+  int inspected = 0;
+  for (; word < nwords; word += nwarps) {
+    const Index row = word*32 + lane;
+    const unsigned int mword = __ldg(mask_bits + word);
+    const bool mbit = (mword >> lane) & 1u;
+    const bool active = (row < nrows) && (UseScmp ? !mbit : mbit);
+    bool found = false;
+    if (active) {
+      Index k         = __ldg(rowptr + row);
+      const Index end = __ldg(rowptr + row + 1);
+      for (; k < end; ++k) {
+        const Index col = __ldg(colind + k);
+        ++inspected;
+        if ((__ldg(probe + (col >> 5)) >> (col & 31)) & 1u) {
+          found = true;
+          if (UseEarlyExit) break;
+        }
+      }
+    }
+    const unsigned int out = __ballot_sync(GB_FULL_MASK, found);
+    if (lane == 0) w_bits[word] = out;
+    if (row < nrows) w[row] = found ? static_cast<W>(1) : static_cast<W>(0);
+    found_total += found ? 1 : 0;
+  }
+  int total = blockSum<GB_PULL_NT>(found_total, s_red);
+  if (threadIdx.x == 0 && total)
+    atomicAdd(discovered, static_cast<unsigned long long>(total));
   int insp = blockSum<GB_PULL_NT>(inspected, s_red);
   if (threadIdx.x == 0 && insp && inspected_bytes != NULL)
     atomicAdd(inspected_bytes, 4ull*static_cast<unsigned long long>(insp));

@@ -81,6 +81,32 @@ __global__ void denseToBitmapKernel(unsigned int* __restrict__ bits,
   }
 }
 
+// u[i] = bit i of bits ? 1 : 0   (inverse of denseToBitmapKernel for 0/1 data)
+template <typename T>
+__global__ void bitmapToDenseKernel(T* __restrict__ u,
+                                    const unsigned int* __restrict__ bits,
+                                    Index n) {
+  Index i = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  for (; i < n; i += stride)
+    u[i] = ((bits[i >> 5] >> (i & 31)) & 1u) ? static_cast<T>(1)
+                                             : static_cast<T>(0);
+}
+
+// *counter += popcount of the first nwords words
+__global__ void popcountKernel(unsigned long long* counter,
+                               const unsigned int* __restrict__ bits,
+                               Index nwords) {
+  __shared__ int s_red[256/32];
+  Index i = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  int local = 0;
+  for (; i < nwords; i += stride) local += __popc(bits[i]);
+  int total = blockSum<256>(local, s_red);
+  if (threadIdx.x == 0 && total)
+    atomicAdd(counter, static_cast<unsigned long long>(total));
+}
+
 // deg[i] = rowptr[f[i]+1] - rowptr[f[i]] for i < nf, deg[nf] = 0.
 // (reference indirectScanKernel, kernels/util.hpp:150-165)
 __global__ void frontierDegreeKernel(Index* __restrict__ deg,

@@ -133,6 +133,23 @@ class SparseMatrix {
   bool symmetric_;
 
   SparseMatrixFormat format_;
+
+  // Cached merge-path tile partitions of the pull SpMV (one per traversed
+  // structure: 0 = CSR rows, 1 = CSC columns), valid for the rowptr they were
+  // computed from.
+  Index*       d_spmv_tiles_[2];
+  const Index* spmv_tiles_key_[2];
+  Index        spmv_tiles_nvals_[2];
+  int          spmv_tiles_count_[2];
+  void dropSpmvTiles() {
+    for (int k = 0; k < 2; ++k) {
+      if (d_spmv_tiles_[k] != NULL) gbFree(d_spmv_tiles_[k]);
+      d_spmv_tiles_[k] = NULL;
+      spmv_tiles_key_[k] = NULL;
+      spmv_tiles_nvals_[k] = -1;
+      spmv_tiles_count_[k] = 0;
+    }
+  }
 };
 
 template <typename T>
@@ -148,6 +165,12 @@ void SparseMatrix<T>::init(Index nrows, Index ncols) {
   cscval_ownership_ = false;
   symmetric_ = false;
   format_ = getEnv("GRB_SPARSE_MATRIX_FORMAT", GrB_SPARSE_MATRIX_CSRCSC);
+  for (int k = 0; k < 2; ++k) {
+    d_spmv_tiles_[k] = NULL;
+    spmv_tiles_key_[k] = NULL;
+    spmv_tiles_nvals_[k] = -1;
+    spmv_tiles_count_[k] = 0;
+  }
 }
 
 template <typename T>
@@ -167,6 +190,7 @@ void SparseMatrix<T>::freeHost() {
 
 template <typename T>
 void SparseMatrix<T>::freeDevice() {
+  dropSpmvTiles();
   if (csc_ownership_) {
     if (d_cscColPtr_ && d_cscColPtr_ != d_csrRowPtr_) gbFree(d_cscColPtr_);
     if (d_cscRowInd_ && d_cscRowInd_ != d_csrColInd_) gbFree(d_cscRowInd_);
@@ -224,7 +248,7 @@ Info SparseMatrix<T>::dup(const SparseMatrix* rhs) {
     if (nvals_ > 0)
       CUDA_CALL(cudaMemcpyAsync(d_cscVal_, rhs->d_cscVal_,
           static_cast<size_t>(nvals_)*sizeof(T), cudaMemcpyDeviceToDevice, s));
-    if (!symmetric_) {
+    if (!symmetric_ && rhs->d_cscColPtr_ != NULL && rhs->d_cscRowInd_ != NULL) {
       CUDA_CALL(cudaMemcpyAsync(d_cscColPtr_, rhs->d_cscColPtr_,
           (ncols_+1)*sizeof(Index), cudaMemcpyDeviceToDevice, s));
       if (nvals_ > 0)

@@ -20,9 +20,11 @@
 namespace graphblas {
 namespace backend {
 
-// Generic SpMV into `out` (raw result, no mask/accum).  2 launches.
+// Generic SpMV into `out` (raw result, no mask/accum).  2 launches (+1 the first
+// time a matrix is used, to compute its tile partition).
 template <typename W, typename a, typename U, typename SemiringT>
 Info spmvMergeLaunch(W*           out,
+                     const Index* tile_rows,
                      SemiringT    op,
                      const Index* rowptr,
                      const Index* colind,
@@ -47,11 +49,11 @@ Info spmvMergeLaunch(W*           out,
   const double alg_bytes = 8.0*nnz + 12.0*nrows + 4.0;
   profiler().begin(GB_PROF_SPMV_MERGE, s);
   if (aligned)
-    spmvMergeKernel<true><<<nctas, GB_SPMV_NT, 0, s>>>(out, carry_row,
+    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, true><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
         extractMul(op), extractAdd(op));
   else
-    spmvMergeKernel<false><<<nctas, GB_SPMV_NT, 0, s>>>(out, carry_row,
+    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
         extractMul(op), extractAdd(op));
   GB_KERNEL_CHECK();
@@ -115,42 +117,81 @@ Info spmv(DenseVector<W>*        w,
     CHECK(mask->getStorage(&mask_vec_type));
 
     if (mask_vec_type == GrB_DENSE) {
-      const M* mask_val = mask->dense_.d_val_;
       unsigned long long* ctr = w->countCell();
       CUDA_CALL(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
-      const int grid = gridFor(A_nrows, GB_PULL_NT, 8);
 
       int variant = 0;
       variant |= use_scmp          ? 4 : 0;
       variant |= desc->earlyexit() ? 2 : 0;
       variant |= desc->opreuse()   ? 1 : 0;
 
-#define GB_LAUNCH_PULL(SC, EE, OR)                                           \
-      spmvMaskedOrPullKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(        \
-          w->d_val_, mask_val, op.identity(), A_nrows, A_csrRowPtr,          \
-          A_csrColInd, u_t->d_val_, ctr, prof_cell)
       unsigned long long* prof_cell = NULL;
       if (profiler().enabled) {
         profiler().ensureCells();
         prof_cell = profiler().d_cells + GB_PROF_PULL_BOOL;
       }
-      profiler().begin(GB_PROF_PULL_BOOL, s);
-      switch (variant) {
-        case 0: GB_LAUNCH_PULL(false, false, false); break;
-        case 1: GB_LAUNCH_PULL(false, false, true ); break;
-        case 2: GB_LAUNCH_PULL(false, true,  false); break;
-        case 3: GB_LAUNCH_PULL(false, true,  true ); break;
-        case 4: GB_LAUNCH_PULL(true,  false, false); break;
-        case 5: GB_LAUNCH_PULL(true,  false, true ); break;
-        case 6: GB_LAUNCH_PULL(true,  true,  false); break;
-        case 7: GB_LAUNCH_PULL(true,  true,  true ); break;
-        default: break;
-      }
+
+      // Bitmap form whenever the Boolean semiring's identity is 0 (the test
+      // "u[col] != identity" is then exactly a bit of u's shadow).  The shadows
+      // of the visited mask and of the frontier are kept current by fill(),
+      // assign() and this kernel itself, so inside a BFS no conversion pass runs;
+      // a stale shadow costs one 4n-byte pass here.
+      const bool bits_form = (op.identity() == static_cast<U>(0));
+      double fixed_bytes;
+      if (bits_form) {
+        DenseVector<M>* mask_dense =
+            const_cast<DenseVector<M>*>(&mask->dense_);
+        const unsigned int* mask_bits = mask_dense->ensureBits();
+        const unsigned int* u_bits =
+            desc->opreuse() ? mask_bits : u_t->ensureBits();
+        unsigned int* w_bits = w->bitsStorage();
+        const int grid = gridFor(A_nrows, GB_PULL_NT, 8);
+#define GB_LAUNCH_PULL(SC, EE, OR)                                           \
+        spmvMaskedOrPullBitsKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(  \
+            w->d_val_, w_bits, mask_bits, u_bits, A_nrows, A_csrRowPtr,      \
+            A_csrColInd, ctr, prof_cell)
+        profiler().begin(GB_PROF_PULL_BOOL, s);
+        switch (variant) {
+          case 0: GB_LAUNCH_PULL(false, false, false); break;
+          case 1: GB_LAUNCH_PULL(false, false, true ); break;
+          case 2: GB_LAUNCH_PULL(false, true,  false); break;
+          case 3: GB_LAUNCH_PULL(false, true,  true ); break;
+          case 4: GB_LAUNCH_PULL(true,  false, false); break;
+          case 5: GB_LAUNCH_PULL(true,  false, true ); break;
+          case 6: GB_LAUNCH_PULL(true,  true,  false); break;
+          case 7: GB_LAUNCH_PULL(true,  true,  true ); break;
+          default: break;
+        }
 #undef GB_LAUNCH_PULL
+        // rowptr + mask bits + output floats + output bits
+        fixed_bytes = 4.0*(A_nrows + 1) + 4.0*A_nrows + 0.25*A_nrows;
+      } else {
+        const M* mask_val = mask->dense_.d_val_;
+        const int grid = gridFor(A_nrows, GB_PULL_NT, 8);
+#define GB_LAUNCH_PULL(SC, EE, OR)                                           \
+        spmvMaskedOrPullKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(      \
+            w->d_val_, mask_val, op.identity(), A_nrows, A_csrRowPtr,        \
+            A_csrColInd, u_t->d_val_, ctr, prof_cell)
+        profiler().begin(GB_PROF_PULL_BOOL, s);
+        switch (variant) {
+          case 0: GB_LAUNCH_PULL(false, false, false); break;
+          case 1: GB_LAUNCH_PULL(false, false, true ); break;
+          case 2: GB_LAUNCH_PULL(false, true,  false); break;
+          case 3: GB_LAUNCH_PULL(false, true,  true ); break;
+          case 4: GB_LAUNCH_PULL(true,  false, false); break;
+          case 5: GB_LAUNCH_PULL(true,  false, true ); break;
+          case 6: GB_LAUNCH_PULL(true,  true,  false); break;
+          case 7: GB_LAUNCH_PULL(true,  true,  true ); break;
+          default: break;
+        }
+#undef GB_LAUNCH_PULL
+        fixed_bytes = 4.0*(A_nrows + 1) + 8.0*A_nrows;
+      }
       GB_KERNEL_CHECK();
-      // rowptr + mask + output; the inspected colind bytes are added on device
-      profiler().end(GB_PROF_PULL_BOOL, s, 4.0*(A_nrows + 1) + 8.0*A_nrows);
+      // the inspected colind bytes are added on the device
+      profiler().end(GB_PROF_PULL_BOOL, s, fixed_bytes);
       w->touched();
+      w->bits_valid_ = bits_form;
       // The kernel wrote 0/1 and counted the ones: the next convert() or
       // a PlusMonoid reduce can reuse the count (one 8-byte read, no pass).
       w->count_pending_ = true;
@@ -172,8 +213,29 @@ Info spmv(DenseVector<W>*        w,
     else
       w_val = w->d_val_;
 
-    CHECK(spmvMergeLaunch(w_val, op, A_csrRowPtr, A_csrColInd, A_csrVal,
-        u_t->d_val_, A_nrows, A->nvals_, desc));
+    // Tile partition of this structure, computed once per matrix.
+    SparseMatrix<a>* A_t = const_cast<SparseMatrix<a>*>(A);
+    const int which = use_tran ? 1 : 0;
+    const long long merge_total = static_cast<long long>(A_nrows) + A->nvals_;
+    const int ntiles = static_cast<int>((merge_total + GB_SPMV_TILE - 1)/
+        GB_SPMV_TILE);
+    if (A_t->d_spmv_tiles_[which] == NULL ||
+        A_t->spmv_tiles_key_[which] != A_csrRowPtr ||
+        A_t->spmv_tiles_nvals_[which] != A->nvals_ ||
+        A_t->spmv_tiles_count_[which] != ntiles) {
+      if (A_t->d_spmv_tiles_[which] != NULL) gbFree(A_t->d_spmv_tiles_[which]);
+      A_t->d_spmv_tiles_[which] = reinterpret_cast<Index*>(
+          gbMalloc((static_cast<size_t>(ntiles) + 1)*sizeof(Index)));
+      spmvMergePartitionKernel<<<(ntiles + 256)/256, 256, 0, s>>>(
+          A_t->d_spmv_tiles_[which], A_csrRowPtr, A_nrows, A->nvals_, ntiles,
+          GB_SPMV_TILE);
+      GB_KERNEL_CHECK();
+      A_t->spmv_tiles_key_[which]   = A_csrRowPtr;
+      A_t->spmv_tiles_nvals_[which] = A->nvals_;
+      A_t->spmv_tiles_count_[which] = ntiles;
+    }
+    CHECK(spmvMergeLaunch(w_val, A_t->d_spmv_tiles_[which], op, A_csrRowPtr,
+        A_csrColInd, A_csrVal, u_t->d_val_, A_nrows, A->nvals_, desc));
 
     if (use_mask) {
       Storage mask_vec_type;

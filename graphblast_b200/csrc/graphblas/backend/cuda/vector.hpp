@@ -311,14 +311,21 @@ Info Vector<T>::sparse2dense(T identity, Descriptor* desc) {
   CHECK(setStorage(GrB_DENSE));
   const Index nvals = sparse_.nvals_;
 
+  bool keep_bits = false;
   if (desc == NULL || !desc->opreuse()) {
     CHECK(dense_.fill(identity));
     if (nvals > 0) {
       const int nt = 256;
-      if (desc != NULL && desc->struconly())
+      if (desc != NULL && desc->struconly()) {
         scatterConstKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
             dense_.d_val_, sparse_.d_ind_, (T)1, nvals);
-      else
+        if (identity == static_cast<T>(0) && dense_.bits_valid_) {
+          GB_KERNEL_CHECK();
+          scatterBitsKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
+              dense_.d_bits_, sparse_.d_ind_, nvals);
+          keep_bits = true;
+        }
+      } else
         scatterValsKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
             dense_.d_val_, sparse_.d_ind_, sparse_.d_val_, nvals);
       GB_KERNEL_CHECK();
@@ -329,6 +336,7 @@ Info Vector<T>::sparse2dense(T identity, Descriptor* desc) {
   dense_.need_update_  = true;
   dense_.nnz_          = nvals;
   dense_.nnz_valid_    = false;
+  dense_.bits_valid_   = keep_bits;
   return GrB_SUCCESS;
 }
 
@@ -348,7 +356,21 @@ Info Vector<T>::dense2sparse(T identity, Descriptor* desc) {
       GrB_LOAD_BALANCE_MERGE);
 
   Index count;
-  if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
+  if (dense_.bits_valid_ && identity == static_cast<T>(0)) {
+    // Compact the bitmap shadow: n/32 words instead of n values.
+    const Index nwords = (n + 31)/32;
+    if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
+      DenseBitsCompactSource<T, true> src;
+      src.bits = dense_.d_bits_; src.u = dense_.d_val_;
+      src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+      count = compactOrdered(src, nwords, desc);
+    } else {
+      DenseBitsCompactSource<T, false> src;
+      src.bits = dense_.d_bits_; src.u = dense_.d_val_;
+      src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+      count = compactOrdered(src, nwords, desc);
+    }
+  } else if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
     DenseCompactSource<T, true> src;
     src.u = dense_.d_val_; src.identity = identity; src.n = n;
     src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;

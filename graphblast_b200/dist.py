@@ -1,0 +1,362 @@
+"""1-D row-partitioned multi-GPU traversal.
+
+One process per GPU (torchrun), `torch.distributed` for rendezvous and the NCCL
+collective.  Rank p owns the output vertices [bounds[p], bounds[p+1]) and stores
+the rows of A^T for them as a rectangular local matrix M (n_local x n, CSR for the
+pull direction, CSC for the push direction), so both directions produce only
+owned outputs and no reduction across ranks is needed.  After each local mxv the
+new frontier is exchanged with ONE collective: every rank contributes the bitmap
+of its owned slice (n/8 bytes in total for n vertices, plus its count), and every
+rank receives the whole bitmap = the replicated input vector of the next level.
+
+The reference has no distributed path at all (SURVEY.md §2 "Parallelism
+strategies": none); the per-level operation sequence is the reference's BFS loop
+(graphblas/algorithm/bfs.hpp:46-79) applied to the owned slice:
+    assign(v_own<f_own> = level); f2_own<!v_own> = M (||.&&) f_global; exchange.
+
+The generic driver `run_bfs` only talks to a `LocalOps` object and a `Comm`
+object, so its partition / exchange / termination logic is testable on CPU with
+the gloo backend and a host-side stand-in for the local operations (tests/).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+
+# ---------------------------------------------------------------------------
+# Partition
+# ---------------------------------------------------------------------------
+
+def partition_bounds(rowptr, world, align=1024):
+    """Contiguous vertex ranges with (nearly) equal numbers of stored entries;
+    every boundary is a multiple of `align` (>= 32, so bitmap slices are whole
+    words).  rowptr: 1-D integer tensor/array of length n+1.  Returns a list of
+    world+1 ints."""
+    rp = rowptr if isinstance(rowptr, np.ndarray) else rowptr.cpu().numpy()
+    n = len(rp) - 1
+    nnz = int(rp[-1])
+    assert align % 32 == 0
+    bounds = [0]
+    for p in range(1, world):
+        target = nnz * p // world
+        v = int(np.searchsorted(rp, target, side="left"))
+        v = min(n, max(bounds[-1], (v + align // 2) // align * align))
+        bounds.append(v)
+    bounds.append(n)
+    for p in range(world):
+        if bounds[p + 1] < bounds[p]:
+            bounds[p + 1] = bounds[p]
+    return bounds
+
+
+def words_of(lo, hi):
+    return (hi - lo + 31) // 32
+
+
+def local_slice(rowptr, colind, lo, hi, n):
+    """CSR and CSC (device tensors when the inputs are) of rows [lo, hi) of a
+    structurally symmetric matrix, i.e. of A^T restricted to the owned outputs.
+    Returns rp_local[n_local+1], ci_local[nnz_l], colptr[n+1], rowind[nnz_l]."""
+    e0 = int(rowptr[lo])
+    e1 = int(rowptr[hi])
+    rp_local = (rowptr[lo:hi + 1] - rowptr[lo]).to(torch.int32).contiguous()
+    ci_local = colind[e0:e1].contiguous()
+    nl = hi - lo
+    rows = torch.repeat_interleave(
+        torch.arange(nl, device=colind.device, dtype=torch.int64),
+        (rp_local[1:] - rp_local[:-1]).to(torch.int64))
+    key = ci_local.to(torch.int64) * nl + rows
+    order = torch.argsort(key)
+    rowind = rows[order].to(torch.int32).contiguous()
+    counts = torch.bincount(ci_local.to(torch.int64), minlength=n)
+    colptr = torch.zeros(n + 1, dtype=torch.int64, device=colind.device)
+    torch.cumsum(counts, 0, out=colptr[1:])
+    return rp_local, ci_local, colptr.to(torch.int32).contiguous(), rowind
+
+
+# ---------------------------------------------------------------------------
+# Frontier exchange
+# ---------------------------------------------------------------------------
+
+class Comm(object):
+    """Bitmap all-gather with uneven owned slices.  Each rank sends a fixed-size
+    record: max_words bitmap words followed by two words holding its 64-bit
+    count; the records are unpacked into the global bitmap (slices are whole
+    words because every boundary is a multiple of 32)."""
+
+    def __init__(self, bounds, device, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.bounds = bounds
+        self.world = len(bounds) - 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.words = [words_of(bounds[p], bounds[p + 1]) for p in range(self.world)]
+        self.max_words = max(self.words) if self.words else 0
+        self.rec = self.max_words + 2
+        self.device = torch.device(device)
+        self.sendbuf = torch.zeros(self.rec, dtype=torch.int32, device=device)
+        self.recvbuf = torch.zeros(self.rec * self.world, dtype=torch.int32,
+                                   device=device)
+        self.total_words = sum(self.words)
+        self.gbits = torch.zeros(self.total_words + 8, dtype=torch.int32,
+                                 device=device)
+        self.offsets = np.concatenate([[0], np.cumsum(self.words)]).tolist()
+
+    def exchange(self, local_bits, local_count):
+        """local_bits: int32 tensor with this rank's bitmap words (>= words[rank]).
+        Returns (global bitmap tensor, global count)."""
+        w = self.words[self.rank]
+        self.sendbuf[:w] = local_bits[:w]
+        self.sendbuf[self.max_words] = int(local_count) & 0x7fffffff
+        self.sendbuf[self.max_words + 1] = int(local_count) >> 31
+        if self.world > 1:
+            if self.device.type == "cpu":      # gloo (CPU tests)
+                parts = list(self.recvbuf.view(self.world, self.rec).unbind(0))
+                parts = [p.clone() for p in parts]
+                self.dist.all_gather(parts, self.sendbuf, group=self.group)
+                self.recvbuf.copy_(torch.cat(parts))
+            else:
+                self.dist.all_gather_into_tensor(self.recvbuf, self.sendbuf,
+                                                 group=self.group)
+        else:
+            self.recvbuf.copy_(self.sendbuf)
+        rec = self.recvbuf.view(self.world, self.rec)
+        for p in range(self.world):
+            o = self.offsets[p]
+            self.gbits[o:o + self.words[p]] = rec[p, :self.words[p]]
+        counts = rec[:, self.max_words:].to("cpu")            # one small D2H
+        total = int((counts[:, 0].to(torch.int64) +
+                     (counts[:, 1].to(torch.int64) << 31)).sum())
+        return self.gbits, total
+
+
+# ---------------------------------------------------------------------------
+# Local operations through the C ABI (GPU)
+# ---------------------------------------------------------------------------
+
+class GpuLocalOps(object):
+    """The owned slice's part of one BFS level, as GraphBLAS operations of this
+    library: assign on the owned visited vector and a masked mxv with the
+    rectangular local matrix."""
+
+    def __init__(self, gb, n, lo, hi, rp_local, ci_local, colptr, rowind, desc):
+        self.gb = gb
+        self.n, self.lo, self.hi = n, lo, hi
+        self.nl = hi - lo
+        self.desc = desc
+        dev = ci_local.device
+        self._keep = [rp_local, ci_local, colptr, rowind]
+        self.val = torch.ones(max(ci_local.numel(), 1), dtype=torch.float32,
+                              device=dev)
+        self.cscval = torch.ones(max(ci_local.numel(), 1), dtype=torch.float32,
+                                 device=dev)
+        self.M = gb.Matrix(max(self.nl, 1), n)
+        if self.nl > 0 and ci_local.numel() > 0:
+            self.M.build_device_csr(rp_local, ci_local, self.val,
+                                    ci_local.numel(), colptr, rowind,
+                                    self.cscval, symmetric=False)
+            self.has_edges = True
+        else:
+            self.has_edges = False
+        nl1 = max(self.nl, 1)
+        self.v = gb.Vector(nl1)
+        self.f_own = gb.Vector(nl1)
+        self.f2 = gb.Vector(nl1)
+        self.f_global = gb.Vector(n)
+        self.local_bits = torch.zeros(words_of(0, nl1) + 8, dtype=torch.int32,
+                                      device=dev)
+        self.lib = gb._lib.load()
+
+    def reset(self):
+        self.v.fill(0.0)
+
+    def assign_level(self, gbits, word_lo, level):
+        """v_own<f_own> = level, f_own = owned slice of the global frontier."""
+        if self.nl == 0:
+            return
+        ptr = gbits.data_ptr() + 4 * word_lo
+        rc = self.lib.gb200_vector_import_bits(self.f_own._h, C.c_void_p(ptr), -1)
+        assert rc == 0, rc
+        self.gb.assign(self.v, self.f_own, None, float(level), None, self.nl,
+                       self.desc)
+
+    def expand(self, gbits, gcount):
+        """f2_own<!v_own> = M (||.&&) f_global; returns (bitmap words, count)."""
+        if self.nl == 0 or not self.has_edges:
+            self.local_bits.zero_()
+            return self.local_bits, 0
+        rc = self.lib.gb200_vector_import_bits(self.f_global._h,
+                                               C.c_void_p(gbits.data_ptr()),
+                                               int(gcount))
+        assert rc == 0, rc
+        gb = self.gb
+        self.desc.toggle(gb.Desc_field.GrB_MASK)
+        try:
+            gb.mxv(self.f2, self.v, None, gb.LogicalOrAndSemiring, self.M,
+                   self.f_global, self.desc)
+        finally:
+            self.desc.toggle(gb.Desc_field.GrB_MASK)
+        count = C.c_longlong(0)
+        rc = self.lib.gb200_vector_export_bits(
+            self.f2._h, C.c_void_p(self.local_bits.data_ptr()), C.byref(count))
+        assert rc == 0, rc
+        return self.local_bits, count.value
+
+    def levels(self):
+        if self.nl == 0:
+            return np.zeros(0, dtype=np.float32)
+        return self.v.extractTuples()[:self.nl]
+
+
+# ---------------------------------------------------------------------------
+# Driver
+# ---------------------------------------------------------------------------
+
+def run_bfs(ops, comm, source, max_levels=10000):
+    """Level-synchronous BFS over the 1-D partition.  Returns the number of
+    levels executed."""
+    bounds = comm.bounds
+    rank = comm.rank
+    lo = bounds[rank]
+    word_lo = comm.offsets[rank]
+    ops.reset()
+    # level-1 frontier: the source, published by its owner through the exchange
+    nw = comm.words[rank]
+    seed = torch.zeros(max(nw, 1) + 8, dtype=torch.int32, device=comm.device)
+    own = 1 if (bounds[rank] <= source < bounds[rank + 1]) else 0
+    if own:
+        rel = source - lo
+        bit = rel & 31
+        seed[rel >> 5] = (1 << bit) if bit < 31 else -(1 << 31)
+    gbits, total = comm.exchange(seed, own)
+    level = 0
+    while total > 0 and level < max_levels:
+        level += 1
+        ops.assign_level(gbits, word_lo, level)
+        local_bits, count = ops.expand(gbits, total)
+        gbits, total = comm.exchange(local_bits, count)
+    return level
+
+
+def bench_distributed(args, world, rank, local_rank):
+    """bench.py body for WORLD_SIZE > 1: strong scaling of the headline BFS."""
+    import os
+    import time
+    import torch.distributed as dist
+    import graphblast_b200 as gb
+    from graphblast_b200 import graphs
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    n = 1 << args.scale
+    src, dst = graphs.rmat_edges(args.scale, args.edgefactor, seed=args.seed,
+                                 device=dev)
+    rowptr, colind = graphs.build_csr(n, src, dst, undirected=True)
+    del src, dst
+    nnz = int(colind.numel())
+    deg = rowptr[1:] - rowptr[:-1]
+    source = int(torch.argmax(deg).item())
+    bounds = partition_bounds(rowptr, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    rp_l, ci_l, colptr, rowind = local_slice(rowptr, colind, lo, hi, n)
+    h_rowptr = rowptr.cpu().numpy() if rank == 0 else None
+    h_colind = colind.cpu().numpy() if rank == 0 else None
+    nnz_local = int(ci_l.numel())
+    del rowptr, colind, deg
+    torch.cuda.empty_cache()
+
+    desc = gb.Descriptor(mxvmode=0, struconly=1, opreuse=0, earlyexit=1)
+    ops = GpuLocalOps(gb, n, lo, hi, rp_l, ci_l, colptr, rowind, desc)
+    comm = Comm(bounds, dev)
+
+    for _ in range(max(args.warmup, 1)):
+        run_bfs(ops, comm, source)
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    lib = gb._lib.load()
+    launches0 = C.c_ulonglong(0)
+    lib.gb200_launch_count(C.byref(launches0))
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    levels = 0
+    for _ in range(args.steps):
+        levels = run_bfs(ops, comm, source)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1), wall_ms], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches1 = C.c_ulonglong(0)
+    lib.gb200_launch_count(C.byref(launches1))
+    ms_per_step = float(ms[0].item()) / args.steps
+
+    # parity: gather the owned level slices on rank 0 and compare with the CPU code
+    mine = torch.from_numpy(ops.levels().astype(np.float32)).to(dev)
+    sizes = [bounds[p + 1] - bounds[p] for p in range(world)]
+    pad = max(sizes)
+    buf = torch.zeros(pad, dtype=torch.float32, device=dev)
+    buf[:mine.numel()] = mine
+    allv = torch.zeros(pad * world, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(allv, buf)
+    parity = None
+    cpu_baseline = None
+    nnz_per_rank = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
+    gathered = [torch.zeros_like(nnz_per_rank) for _ in range(world)]
+    dist.all_gather(gathered, nnz_per_rank)
+    if rank == 0:
+        got = np.concatenate([allv[p * pad:p * pad + sizes[p]].cpu().numpy()
+                              for p in range(world)]).astype(np.int32)
+        if not args.no_cpu_baseline:
+            import sys
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
+                os.path.abspath(__file__))), "tests"))
+            import oracle_binding as orc
+            kind = "reference" if orc.ref() is not None else "port"
+            fn = orc.ref_bfs if kind == "reference" else orc.bfs
+            t0 = time.perf_counter()
+            want = fn(h_rowptr, h_colind, source)
+            dt = time.perf_counter() - t0
+            parity = bool(np.array_equal(got, want))
+            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
+                            "cores": 1, "kind": kind, "ms": dt * 1e3,
+                            "host_cores_total": os.cpu_count(),
+                            "sample": "one full BFS of the same graph"}
+    result = {
+        "metric": "MTEPS", "value": nnz / (ms_per_step * 1e3),
+        "unit": "MTEPS (stored entries of A / traversal time x 1e-6)",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": "direction-optimised BFS (LogicalOrAnd mxv, push<->pull) "
+                        "on R-MAT scale-%d ef-%d seed %d, symmetrised"
+                        % (args.scale, args.edgefactor, args.seed),
+            "n": n, "nnz": nnz, "source": source, "levels": levels,
+            "partition": "1-D nnz-balanced row slices, bounds %s" % bounds,
+            "nnz_per_rank": [int(g.item()) for g in gathered],
+            "exchange": "NCCL all-gather of the frontier bitmap "
+                        "(%d bytes per level) + counts" % (4 * comm.rec * world),
+            "flags": "--mxvmode 0 --struconly 1 --earlyexit 1 (opreuse off: the "
+                     "visited mask is local)",
+            "l2_policy": "inputs larger than L2"},
+        "e2e": {"value": nnz / (float(ms[1].item()) / args.steps * 1e3),
+                "unit": "MTEPS", "h2d_bytes_per_step": 4,
+                "d2h_bytes_per_step": 8 * world,
+                "note": "host wall clock around the same K steps (max over "
+                        "ranks), including the per-level count read-back"},
+        "gpu_launches": int(launches1.value - launches0.value),
+        "cpu_baseline": cpu_baseline,
+        "parity_vs_cpu_reference": parity,
+    }
+    dist.destroy_process_group()
+    return result

@@ -198,6 +198,17 @@ int gb200_pr(gb200_vector_t p, gb200_matrix_t A, float alpha, float eps,
 int gb200_tc(long long* ntris, gb200_matrix_t A, gb200_matrix_t B,
              gb200_desc_t desc, float* tight_ms);               /* algorithm/tc.hpp:15-54 */
 
+/* ---- Frontier exchange helpers for the 1-D row-partitioned multi-GPU path ----
+ * (the reference has no distributed path.)  A Boolean frontier
+ * travels between ranks as a bitmap, n/8 bytes for n vertices. */
+/* Bitmap (bit == value != 0) of v into DEVICE words d_bits[(size+31)/32]; works
+ * for dense and sparse storage.  count_out (may be NULL) receives the popcount. */
+int gb200_vector_export_bits(gb200_vector_t v, uint32_t* d_bits, long long* count_out);
+/* v becomes a dense 0/1 vector with the given bitmap (DEVICE words).
+ * nnz >= 0 tells the number of set bits (saves the counting pass of the next
+ * direction decision); pass -1 when unknown. */
+int gb200_vector_import_bits(gb200_vector_t v, const uint32_t* d_bits, long long nnz);
+
 /* ---- Measurement hooks (bench.py; no reference counterpart) --------------- */
 /* Hot-kernel kinds: 0 merge-path SpMV (pull, generic semiring), 1 fused Boolean
  * pull, 2 push (SpMSpV expand), 3 masked SpGEMM.  When enabled every launch of

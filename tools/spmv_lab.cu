@@ -1,0 +1,231 @@
+// tools/spmv_lab.cu — kernel laboratory for the pull-direction merge-path SpMV.
+// Generates an R-MAT graph on the device (same generator as gb200_rmat_edges),
+// builds the CSR with thrust, and times configurations of spmvMergeKernelT plus
+// two reference points (pure streaming of colind/val, streaming + gather without
+// the merge).  Prints one line per variant: ms, algorithmic GB/s, fraction of the
+// measured HBM peak.  Usage: spmv_lab [scale=22] [edgefactor=16] [reps=5]
+#define GRB_USE_CUDA
+#include <thrust/device_vector.h>
+#include <thrust/sort.h>
+#include <thrust/unique.h>
+#include <thrust/remove.h>
+#include <thrust/scan.h>
+#include <thrust/binary_search.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <boost/program_options.hpp>
+#include "graphblas/graphblas.hpp"
+
+bool debug_;
+bool memory_;
+
+using graphblas::Index;
+using namespace graphblas::backend;
+
+__global__ void rmatKeys(int scale, long long nedges, unsigned long long seed,
+                         unsigned long long* keys) {
+  const unsigned int T1 = 2448131358u, T2 = 3264175144u, T3 = 4080218930u;
+  long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x*blockDim.x;
+  const unsigned long long n = 1ull << scale;
+  for (; e < nedges; e += stride) {
+    unsigned int s = 0, d = 0;
+    for (int l = 0; l < scale; ++l) {
+      unsigned long long z = ((seed << 48) ^ ((unsigned long long)e << 6) ^
+          (unsigned long long)l) + 0x9E3779B97F4A7C15ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z = z ^ (z >> 31);
+      const unsigned int r = (unsigned int)(z >> 32);
+      s = (s << 1) | ((r >= T2) ? 1u : 0u);
+      d = (d << 1) | (((r >= T1 && r < T2) || r >= T3) ? 1u : 0u);
+    }
+    keys[2*e]     = (unsigned long long)s*n + d;
+    keys[2*e + 1] = (unsigned long long)d*n + s;
+  }
+}
+
+struct IsLoop {
+  unsigned long long n;
+  __host__ __device__ bool operator()(unsigned long long k) const {
+    return (k / n) == (k % n);
+  }
+};
+
+__global__ void splitKeys(const unsigned long long* keys, long long nnz,
+                          unsigned long long n, int* rows, int* cols, float* val) {
+  long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x*blockDim.x;
+  for (; i < nnz; i += stride) {
+    rows[i] = (int)(keys[i] / n);
+    cols[i] = (int)(keys[i] % n);
+    val[i]  = (float)(1 + (keys[i]*2654435761ull >> 40) % 64);
+  }
+}
+
+// Reference point 1: stream colind + val with 256-bit loads, no gather.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+streamOnlyKernel(float* out, const int* colind, const float* val, long long nnz) {
+  long long c = (long long)blockIdx.x*NT + threadIdx.x;
+  const long long stride = (long long)gridDim.x*NT;
+  float acc = 0.f;
+  for (; (c + 1)*8 <= nnz; c += stride) {
+    Word8 cw = ldStream256(colind + c*8);
+    Word8 vw = ldStream256(val + c*8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += __int_as_float(vw.w[j]) + (cw.w[j] & 1);
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
+// Reference point 2: stream + gather u[col], no row reduction.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+streamGatherKernel(float* out, const int* colind, const float* val,
+                   const float* u, long long nnz) {
+  long long c = (long long)blockIdx.x*NT + threadIdx.x;
+  const long long stride = (long long)gridDim.x*NT;
+  const uint64_t pol = makeEvictLastPolicy();
+  float acc = 0.f;
+  for (; (c + 1)*8 <= nnz; c += stride) {
+    Word8 cw = ldStream256(colind + c*8);
+    Word8 vw = ldStream256(val + c*8);
+    float uv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) uv[j] = ldGather(u + cw.w[j], pol);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fminf(acc, __int_as_float(vw.w[j]) + uv[j]);
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
+typedef graphblas::MinimumPlusSemiring<float> SR;
+
+template <int NT, int IPT, bool Gather>
+float runMerge(float* w, const int* rowptr, const int* colind, const float* val,
+               const float* u, int n, int nnz, int reps, int carveout) {
+  SR op;
+  const long long total = (long long)n + nnz;
+  const int tile = NT*IPT;
+  const int nctas = (int)((total + tile - 1)/tile);
+  thrust::device_vector<int> tiles(nctas + 1), crow(nctas);
+  thrust::device_vector<float> cval(nctas);
+  spmvMergePartitionKernel<<<(nctas + 256)/256, 256>>>(
+      thrust::raw_pointer_cast(tiles.data()), rowptr, n, nnz, nctas, tile);
+  auto kern = spmvMergeKernelT<NT, IPT, true, Gather, float, float, float,
+      decltype(graphblas::extractMul(op)), decltype(graphblas::extractAdd(op))>;
+  if (carveout >= 0)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         carveout);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(a);
+    kern<<<nctas, NT>>>(w, thrust::raw_pointer_cast(tiles.data()),
+        thrust::raw_pointer_cast(crow.data()),
+        thrust::raw_pointer_cast(cval.data()), rowptr, colind, val, u, n, nnz,
+        op.identity(), graphblas::extractMul(op), graphblas::extractAdd(op));
+    spmvCarryFixupKernel<<<(nctas + 255)/256, 256>>>(w,
+        thrust::raw_pointer_cast(crow.data()),
+        thrust::raw_pointer_cast(cval.data()), nctas, graphblas::extractAdd(op));
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) printf("CUDA error: %s\n", cudaGetErrorString(err));
+  return best;
+}
+
+int main(int argc, char** argv) {
+  const int scale = argc > 1 ? atoi(argv[1]) : 22;
+  const int ef    = argc > 2 ? atoi(argv[2]) : 16;
+  const int reps  = argc > 3 ? atoi(argv[3]) : 5;
+  const double peak = argc > 4 ? atof(argv[4]) : 6547.8;
+  const unsigned long long n = 1ull << scale;
+  const long long nedges = (long long)ef << scale;
+
+  thrust::device_vector<unsigned long long> keys(2*nedges);
+  rmatKeys<<<148*8, 256>>>(scale, nedges, 1ull, thrust::raw_pointer_cast(keys.data()));
+  auto end1 = thrust::remove_if(keys.begin(), keys.end(), IsLoop{n});
+  thrust::sort(keys.begin(), end1);
+  auto end2 = thrust::unique(keys.begin(), end1);
+  const long long nnz = end2 - keys.begin();
+  thrust::device_vector<int> rows(nnz), cols(nnz), rowptr(n + 1);
+  thrust::device_vector<float> val(nnz), u(n), w(n), w2(n);
+  splitKeys<<<148*8, 256>>>(thrust::raw_pointer_cast(keys.data()), nnz, n,
+      thrust::raw_pointer_cast(rows.data()), thrust::raw_pointer_cast(cols.data()),
+      thrust::raw_pointer_cast(val.data()));
+  thrust::lower_bound(rows.begin(), rows.end(), thrust::counting_iterator<int>(0),
+      thrust::counting_iterator<int>((int)n + 1), rowptr.begin());
+  keys.clear(); keys.shrink_to_fit();
+  thrust::sequence(u.begin(), u.end());
+  printf("scale %d: n=%llu nnz=%lld\n", scale, n, nnz);
+  const int* rp = thrust::raw_pointer_cast(rowptr.data());
+  const int* ci = thrust::raw_pointer_cast(cols.data());
+  const float* va = thrust::raw_pointer_cast(val.data());
+  const float* up = thrust::raw_pointer_cast(u.data());
+  float* wp = thrust::raw_pointer_cast(w.data());
+  const double alg = 8.0*nnz + 12.0*n + 4.0;
+  auto report = [&](const char* name, float ms) {
+    printf("%-44s %8.3f ms  %7.0f GB/s  %.3f of peak\n", name, ms,
+           alg/1e6/ms, alg/1e6/ms/peak);
+  };
+
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float ms, best;
+  best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(a);
+    streamOnlyKernel<256><<<148*8, 256>>>(wp, ci, va, nnz);
+    cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms < best) best = ms;
+  }
+  report("stream colind+val only (no gather)", best);
+  best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(a);
+    streamGatherKernel<256><<<148*8, 256>>>(wp, ci, va, up, nnz);
+    cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms < best) best = ms;
+  }
+  report("stream + gather (persistent 148x8x256)", best);
+  best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(a);
+    streamGatherKernel<256><<<148*4, 256>>>(wp, ci, va, up, nnz);
+    cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms < best) best = ms;
+  }
+  report("stream + gather (persistent 148x4x256)", best);
+  best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(a);
+    streamGatherKernel<256><<<(int)((nnz/8 + 255)/256), 256>>>(wp, ci, va, up, nnz);
+    cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms < best) best = ms;
+  }
+  report("stream + gather (one chunk per thread)", best);
+
+#define LAB(NT, IPT, G, CARVE)                                               \
+  { char name[96];                                                           \
+    snprintf(name, sizeof(name), "merge NT=%d IPT=%d gather=%d carveout=%d", \
+             NT, IPT, (int)G, CARVE);                                        \
+    report(name, runMerge<NT, IPT, G>(wp, rp, ci, va, up, (int)n, (int)nnz,  \
+                                      reps, CARVE)); }
+  LAB(128, 15, true, -1)
+  LAB(128, 15, false, -1)
+  LAB(256, 7, true, -1)
+  LAB(256, 7, false, -1)
+  LAB(256, 15, true, -1)
+  LAB(128, 7, true, -1)
+  LAB(128, 23, true, -1)
+  LAB(64, 31, true, -1)
+  LAB(128, 15, true, 25)
+  LAB(128, 15, true, 50)
+  LAB(256, 7, true, 50)
+  LAB(512, 7, true, -1)
+  return 0;
+}
