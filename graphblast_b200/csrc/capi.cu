@@ -850,7 +850,7 @@ int gb200_vector_export_bits(gb200_vector_t v, uint32_t* d_bits,
   if (v == NULL || d_bits == NULL) return rc(graphblas::GrB_NULL_POINTER);
   GB200_REQUIRE_DEVICE();
   using namespace graphblas::backend;
-  Vector<float>& b = v->f->vector_;
+  graphblas::backend::Vector<float>& b = v->f->vector_;
   cudaStream_t s = gbStream();
   const size_t nwords = (static_cast<size_t>(b.nsize_) + 31)/32;
   if (b.vec_type_ == graphblas::GrB_DENSE) {
@@ -888,7 +888,7 @@ int gb200_vector_import_bits(gb200_vector_t v, const uint32_t* d_bits,
   if (v == NULL || d_bits == NULL) return rc(graphblas::GrB_NULL_POINTER);
   GB200_REQUIRE_DEVICE();
   using namespace graphblas::backend;
-  Vector<float>& b = v->f->vector_;
+  graphblas::backend::Vector<float>& b = v->f->vector_;
   cudaStream_t s = gbStream();
   Info info = b.setStorage(graphblas::GrB_DENSE);
   if (info != GrB_SUCCESS) return rc(info);
