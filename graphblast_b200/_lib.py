@@ -83,6 +83,7 @@ SIGNATURES = [
     ("gb200_tc", _I, [C.POINTER(_LL), _P, _P, _P, C.POINTER(_F)]),
     ("gb200_rmat_edges", _I, [_I, _LL, _ULL, _LL, _P, _P]),
     ("gb200_vector_export_bits", _I, [_P, _P, C.POINTER(_LL)]),
+    ("gb200_vector_export_bits_async", _I, [_P, _P, _P]),
     ("gb200_vector_import_bits", _I, [_P, _P, _LL]),
     ("gb200_profile_enable", _I, [_I]),
     ("gb200_profile_reset", _I, []),

@@ -883,6 +883,23 @@ int gb200_vector_export_bits(gb200_vector_t v, uint32_t* d_bits,
   return 0;
 }
 
+int gb200_vector_export_bits_async(gb200_vector_t v, uint32_t* d_bits,
+                                   unsigned long long* d_count) {
+  if (v == NULL || d_bits == NULL || d_count == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  int info = gb200_vector_export_bits(v, d_bits, NULL);
+  if (info != 0) return info;
+  using namespace graphblas::backend;
+  cudaStream_t s = gbStream();
+  const size_t nwords =
+      (static_cast<size_t>(v->f->vector_.nsize_) + 31)/32;
+  CUDA_CALL(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
+  popcountKernel<<<gridFor(nwords, 256), 256, 0, s>>>(d_count, d_bits,
+      static_cast<graphblas::Index>(nwords));
+  GB_KERNEL_CHECK();
+  return 0;
+}
+
 int gb200_vector_import_bits(gb200_vector_t v, const uint32_t* d_bits,
                              long long nnz) {
   if (v == NULL || d_bits == NULL) return rc(graphblas::GrB_NULL_POINTER);

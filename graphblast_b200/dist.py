@@ -94,6 +94,7 @@ class Comm(object):
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.words = [words_of(bounds[p], bounds[p + 1]) for p in range(self.world)]
         self.max_words = max(self.words) if self.words else 0
+        self.max_words += self.max_words & 1          # 8-byte aligned count cell
         self.rec = self.max_words + 2
         self.device = torch.device(device)
         self.sendbuf = torch.zeros(self.rec, dtype=torch.int32, device=device)
@@ -104,17 +105,29 @@ class Comm(object):
                                  device=device)
         self.offsets = np.concatenate([[0], np.cumsum(self.words)]).tolist()
 
-    def exchange(self, local_bits, local_count):
-        """local_bits: int32 tensor with this rank's bitmap words (>= words[rank]).
-        Returns (global bitmap tensor, global count)."""
+    def send_bits(self):
+        """Device view the owner writes its bitmap words into."""
+        return self.sendbuf
+
+    def count_ptr(self):
+        """Device address of the 64-bit count cell in the send record."""
+        return self.sendbuf.data_ptr() + 4 * self.max_words
+
+    def set_host_record(self, local_bits, local_count):
+        """Fill the send record from host-known values (seed level, CPU tests)."""
         w = self.words[self.rank]
         self.sendbuf[:w] = local_bits[:w]
-        self.sendbuf[self.max_words] = int(local_count) & 0x7fffffff
-        self.sendbuf[self.max_words + 1] = int(local_count) >> 31
+        tail = torch.tensor([int(local_count) & 0xffffffff,
+                             int(local_count) >> 32], dtype=torch.int64)
+        tail = torch.where(tail >= 2 ** 31, tail - 2 ** 32, tail).to(torch.int32)
+        self.sendbuf[self.max_words:self.max_words + 2] = tail.to(self.device)
+
+    def exchange(self):
+        """All-gathers the send records; returns (global bitmap, global count)."""
         if self.world > 1:
             if self.device.type == "cpu":      # gloo (CPU tests)
-                parts = list(self.recvbuf.view(self.world, self.rec).unbind(0))
-                parts = [p.clone() for p in parts]
+                parts = [torch.zeros(self.rec, dtype=torch.int32)
+                         for _ in range(self.world)]
                 self.dist.all_gather(parts, self.sendbuf, group=self.group)
                 self.recvbuf.copy_(torch.cat(parts))
             else:
@@ -123,12 +136,12 @@ class Comm(object):
         else:
             self.recvbuf.copy_(self.sendbuf)
         rec = self.recvbuf.view(self.world, self.rec)
-        for p in range(self.world):
-            o = self.offsets[p]
-            self.gbits[o:o + self.words[p]] = rec[p, :self.words[p]]
-        counts = rec[:, self.max_words:].to("cpu")            # one small D2H
-        total = int((counts[:, 0].to(torch.int64) +
-                     (counts[:, 1].to(torch.int64) << 31)).sum())
+        torch.cat([rec[p, :self.words[p]] for p in range(self.world)],
+                  out=self.gbits[:self.total_words])
+        tails = rec[:, self.max_words:self.max_words + 2].to("cpu")   # one D2H
+        lo = tails[:, 0].to(torch.int64) & 0xffffffff
+        hi = tails[:, 1].to(torch.int64) & 0xffffffff
+        total = int((lo + (hi << 32)).sum())
         return self.gbits, total
 
 
@@ -165,8 +178,6 @@ class GpuLocalOps(object):
         self.f_own = gb.Vector(nl1)
         self.f2 = gb.Vector(nl1)
         self.f_global = gb.Vector(n)
-        self.local_bits = torch.zeros(words_of(0, nl1) + 8, dtype=torch.int32,
-                                      device=dev)
         self.lib = gb._lib.load()
 
     def reset(self):
@@ -182,11 +193,12 @@ class GpuLocalOps(object):
         self.gb.assign(self.v, self.f_own, None, float(level), None, self.nl,
                        self.desc)
 
-    def expand(self, gbits, gcount):
-        """f2_own<!v_own> = M (||.&&) f_global; returns (bitmap words, count)."""
+    def expand(self, gbits, gcount, comm):
+        """f2_own<!v_own> = M (||.&&) f_global; the new owned frontier goes into
+        comm's send record (bitmap words + device-side count, no host sync)."""
         if self.nl == 0 or not self.has_edges:
-            self.local_bits.zero_()
-            return self.local_bits, 0
+            comm.sendbuf.zero_()
+            return
         rc = self.lib.gb200_vector_import_bits(self.f_global._h,
                                                C.c_void_p(gbits.data_ptr()),
                                                int(gcount))
@@ -198,11 +210,10 @@ class GpuLocalOps(object):
                    self.f_global, self.desc)
         finally:
             self.desc.toggle(gb.Desc_field.GrB_MASK)
-        count = C.c_longlong(0)
-        rc = self.lib.gb200_vector_export_bits(
-            self.f2._h, C.c_void_p(self.local_bits.data_ptr()), C.byref(count))
+        rc = self.lib.gb200_vector_export_bits_async(
+            self.f2._h, C.c_void_p(comm.send_bits().data_ptr()),
+            C.c_void_p(comm.count_ptr()))
         assert rc == 0, rc
-        return self.local_bits, count.value
 
     def levels(self):
         if self.nl == 0:
@@ -230,13 +241,14 @@ def run_bfs(ops, comm, source, max_levels=10000):
         rel = source - lo
         bit = rel & 31
         seed[rel >> 5] = (1 << bit) if bit < 31 else -(1 << 31)
-    gbits, total = comm.exchange(seed, own)
+    comm.set_host_record(seed, own)
+    gbits, total = comm.exchange()
     level = 0
     while total > 0 and level < max_levels:
         level += 1
         ops.assign_level(gbits, word_lo, level)
-        local_bits, count = ops.expand(gbits, total)
-        gbits, total = comm.exchange(local_bits, count)
+        ops.expand(gbits, total, comm)
+        gbits, total = comm.exchange()
     return level
 
 
@@ -248,6 +260,8 @@ def bench_distributed(args, world, rank, local_rank):
     import graphblast_b200 as gb
     from graphblast_b200 import graphs
 
+    # keep stdout to the single JSON line: NCCL's banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 

@@ -204,6 +204,11 @@ int gb200_tc(long long* ntris, gb200_matrix_t A, gb200_matrix_t B,
 /* Bitmap (bit == value != 0) of v into DEVICE words d_bits[(size+31)/32]; works
  * for dense and sparse storage.  count_out (may be NULL) receives the popcount. */
 int gb200_vector_export_bits(gb200_vector_t v, uint32_t* d_bits, long long* count_out);
+/* Same, without any host synchronisation: the 64-bit popcount is written on the
+ * device into d_count (8-byte aligned DEVICE address), e.g. the tail of the
+ * record a rank contributes to the frontier all-gather. */
+int gb200_vector_export_bits_async(gb200_vector_t v, uint32_t* d_bits,
+                                   unsigned long long* d_count);
 /* v becomes a dense 0/1 vector with the given bitmap (DEVICE words).
  * nnz >= 0 tells the number of set bits (saves the counting pass of the next
  * direction decision); pass -1 when unknown. */

@@ -40,7 +40,7 @@ class CpuLocalOps(object):
         own = self._unpack(words, self.nl)
         self.v[own] = level
 
-    def expand(self, gbits, gcount):
+    def expand(self, gbits, gcount, comm):
         frontier = self._unpack(gbits.numpy().astype(np.int32), self.n)
         out = np.zeros(self.nwords * 32, dtype=bool)
         for r in range(self.nl):
@@ -49,7 +49,7 @@ class CpuLocalOps(object):
                 if frontier[nbrs].any():
                     out[r] = True
         words = np.packbits(out, bitorder="little").view(np.int32)
-        return torch.from_numpy(words.copy()), int(out.sum())
+        comm.set_host_record(torch.from_numpy(words.copy()), int(out.sum()))
 
     def levels(self):
         return self.v
@@ -123,6 +123,7 @@ def test_exchange_record_roundtrip_single_rank():
     bounds = [0, 96]
     comm = gdist.Comm(bounds, "cpu")
     words = torch.tensor([5, -2 ** 31, 7], dtype=torch.int32)
-    g, total = comm.exchange(words, 2 ** 33 + 5)
+    comm.set_host_record(words, 2 ** 33 + 5)
+    g, total = comm.exchange()
     assert g[:3].tolist() == [5, -2 ** 31, 7]
     assert total == 2 ** 33 + 5
