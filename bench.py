@@ -431,5 +431,15 @@ def main():
     print(json.dumps(out), flush=True)
 
 
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Native code (NCCL's version
+    banner, printf in libraries) writes to file descriptor 1 directly, so fd 1 is
+    pointed at stderr and Python's sys.stdout keeps the real stdout."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _guard_stdout()
     main()

@@ -16,10 +16,20 @@ Index compactOrdered(Source src, Index nitems, Descriptor* desc) {
   if (nitems <= 0) return 0;
   const int nblocks = static_cast<int>(
       (static_cast<long long>(nitems) + GB_COMPACT_NT - 1) / GB_COMPACT_NT);
-  int* block_counts = reinterpret_cast<int*>(
-      desc->scratch(GB_SCRATCH_BLOCKSUM, static_cast<size_t>(nblocks)*sizeof(int)));
   unsigned long long* ctr = desc->counters() + 1;
   cudaStream_t s = gbStream();
+  static const bool three_pass = getEnv("GB200_COMPACT_3PASS", 0) != 0;
+  if (!three_pass) {
+    // one launch, look-back across CTAs (kernels/compact.cuh)
+    unsigned long long* state = desc->lookback(static_cast<size_t>(nblocks) + 1);
+    desc->lookback_epoch_ = desc->lookback_epoch_ % 0x3ffffffeu + 1u;
+    compactOnePassKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems, state,
+        desc->lookback_epoch_, ctr);
+    GB_KERNEL_CHECK();
+    return static_cast<Index>(runtime().fetch(ctr));
+  }
+  int* block_counts = reinterpret_cast<int*>(
+      desc->scratch(GB_SCRATCH_BLOCKSUM, static_cast<size_t>(nblocks)*sizeof(int)));
   compactCountKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
       block_counts);
   GB_KERNEL_CHECK();

@@ -37,6 +37,7 @@ enum ScratchSlot {
   GB_SCRATCH_VEC_A,       // generic n-sized temporaries
   GB_SCRATCH_VEC_B,
   GB_SCRATCH_CUB,         // cub temp storage
+  GB_SCRATCH_LOOKBACK,    // compaction: ticket cell + per-CTA look-back status
   GB_SCRATCH_NSLOTS
 };
 
@@ -52,7 +53,8 @@ class Descriptor {
     opreuse_(0), memusage_(0), endbit_(0), sort_(0), atomic_(0),
     earlyexit_(0), fusedmask_(0), nthread_(0), ndevice_(0), debug_(0),
     memory_(0), acc_elems_(0), acc_identity_bits_(0), acc_elem_bytes_(0),
-    acc_valid_(false), bits_words_(0), bits_valid_(false) {
+    acc_valid_(false), bits_words_(0), bits_valid_(false),
+    lookback_epoch_(0), lookback_ticket_(0) {
     for (int i = 0; i < GB_SCRATCH_NSLOTS; ++i) {
       slot_ptr_[i]  = NULL;
       slot_size_[i] = 0;
@@ -107,6 +109,25 @@ class Descriptor {
     }
     return slot_ptr_[slot];
   }
+
+  // Look-back state of the single-pass compaction: cell 0 is a ticket counter
+  // that only ever grows, cells 1..nblocks hold (epoch, flag, value) words.  The
+  // block is zeroed when (re)allocated; afterwards nothing is ever reset — each
+  // launch uses a fresh epoch and the ticket base the host has kept count of.
+  unsigned long long* lookback(size_t nblocks) {
+    const size_t bytes = (nblocks + 1)*sizeof(unsigned long long);
+    if (bytes > slot_size_[GB_SCRATCH_LOOKBACK]) {
+      void* p = scratch(GB_SCRATCH_LOOKBACK, bytes);
+      CUDA_CALL(cudaMemsetAsync(p, 0, slot_size_[GB_SCRATCH_LOOKBACK],
+          gbStream()));
+      lookback_epoch_  = 0;
+      lookback_ticket_ = 0;
+    }
+    return reinterpret_cast<unsigned long long*>(
+        slot_ptr_[GB_SCRATCH_LOOKBACK]);
+  }
+  unsigned int       lookback_epoch_;
+  unsigned long long lookback_ticket_;
 
   // Device counters: 64 x 8-byte cells.
   unsigned long long* counters() {

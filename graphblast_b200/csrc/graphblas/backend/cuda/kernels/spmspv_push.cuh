@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(GB_PUSH_NT)
 spmspvPushKernel(unsigned int* __restrict__ bits,
                  W* __restrict__            acc,
                  const M* __restrict__      mask,
+                 const unsigned int* __restrict__ mask_bits,  // or NULL
                  const Index* __restrict__  offs,      // nf+1 scanned degrees
                  const Index* __restrict__  f_ind,
                  const U* __restrict__      f_val,
@@ -118,8 +119,14 @@ spmspvPushKernel(unsigned int* __restrict__ bits,
         }
         const Index col = ldStream(colind + k);
         bool keep = true;
-        if (MaskMode == 1) keep = (__ldg(mask + col) != static_cast<M>(0));
-        if (MaskMode == 2) keep = (__ldg(mask + col) == static_cast<M>(0));
+        if (MaskMode != 0) {
+          // The mask's bitmap shadow (bit == value != 0) when it is current:
+          // a 32x denser gather target than the float array.
+          const bool nonzero = (mask_bits != NULL)
+              ? bitTest(mask_bits, col)
+              : (__ldg(mask + col) != static_cast<M>(0));
+          keep = (MaskMode == 1) ? nonzero : !nonzero;
+        }
         if (keep) {
           if (!StructOnly) {
             const a av = ldStream(val + k);

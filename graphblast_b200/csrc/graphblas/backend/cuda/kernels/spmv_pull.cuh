@@ -266,6 +266,7 @@ __global__ void spmvCarryFixupKernel(W* __restrict__ w,
 // first frontier neighbour when early exit is on).
 // ---------------------------------------------------------------------------
 #define GB_PULL_NT 256
+#define GB_PULL_WPI 4     // mask words (x32 rows) a warp handles per iteration
 
 template <bool UseScmp, bool UseEarlyExit, bool UseOpReuse,
           typename W, typename M, typename U>
@@ -325,6 +326,26 @@ spmvMaskedOrPullKernel(W* __restrict__           w,
 // frontier is written both as 0/1 floats (the vector's storage) and, through one
 // ballot, as its bitmap shadow.
 // ---------------------------------------------------------------------------
+// first[i] = -1 (empty row) | colind[rowptr[i]] | that value with bit 31 set when
+// it is the row's only entry.  Computed once per matrix structure.
+__global__ void pullFirstNeighbourKernel(Index* __restrict__ first,
+                                         const Index* __restrict__ rowptr,
+                                         const Index* __restrict__ colind,
+                                         Index nrows) {
+  Index i = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  for (; i < nrows; i += stride) {
+    const Index beg = __ldg(rowptr + i);
+    const Index len = __ldg(rowptr + i + 1) - beg;
+    Index f = -1;
+    if (len > 0) {
+      f = __ldg(colind + beg);
+      if (len == 1) f |= static_cast<Index>(0x80000000u);
+    }
+    first[i] = f;
+  }
+}
+
 template <bool UseScmp, bool UseEarlyExit, bool UseOpReuse, typename W>
 __global__ void __launch_bounds__(GB_PULL_NT)
 spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
@@ -332,40 +353,82 @@ spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
                            const unsigned int* __restrict__ mask_bits,
                            const unsigned int* __restrict__ u_bits,
                            Index                            nrows,
+                           const Index* __restrict__        first,
                            const Index* __restrict__        rowptr,
                            const Index* __restrict__        colind,
                            unsigned long long*              discovered,
                            unsigned long long*              inspected_bytes) {
   __shared__ int s_red[GB_PULL_NT/32];
   const int lane = threadIdx.x & 31;
-  Index word = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+  const Index warp0  = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
   const Index nwarps = (gridDim.x*blockDim.x) >> 5;
   const Index nwords = (nrows + 31) >> 5;
+  const Index ngroups = (nwords + GB_PULL_WPI - 1)/GB_PULL_WPI;
   const unsigned int* probe = UseOpReuse ? mask_bits : u_bits;
   int found_total = 0;
   int inspected = 0;
-  for (; word < nwords; word += nwarps) {
-    const Index row = word*32 + lane;
-    const unsigned int mword = __ldg(mask_bits + word);
-    const bool mbit = (mword >> lane) & 1u;
-    const bool active = (row < nrows) && (UseScmp ? !mbit : mbit);
-    bool found = false;
-    if (active) {
-      Index k         = __ldg(rowptr + row);
-      const Index end = __ldg(rowptr + row + 1);
-      for (; k < end; ++k) {
-        const Index col = __ldg(colind + k);
-        ++inspected;
-        if ((__ldg(probe + (col >> 5)) >> (col & 31)) & 1u) {
-          found = true;
-          if (UseEarlyExit) break;
-        }
+  // A warp owns GB_PULL_WPI consecutive mask words (128 rows) per iteration and
+  // keeps that many independent load chains (mask word -> first neighbour ->
+  // probe word) in flight per lane: with one word per iteration the late levels
+  // of a traversal, where few rows are still unvisited, were bound by the
+  // latency of one such chain per iteration.
+  for (Index g = warp0; g < ngroups; g += nwarps) {
+    unsigned int mword[GB_PULL_WPI];
+#pragma unroll
+    for (int j = 0; j < GB_PULL_WPI; ++j) {
+      const Index word = g*GB_PULL_WPI + j;
+      mword[j] = (word < nwords) ? __ldg(mask_bits + word)
+                                 : (UseScmp ? 0xffffffffu : 0u);
+    }
+    // One coalesced 4-byte load answers most rows: the first (lowest-index)
+    // neighbour of an R-MAT/social-graph row is usually a hub that is already
+    // visited, and empty rows never touch rowptr/colind at all.  Only a miss on
+    // a row with more entries walks the list (one 32-byte sector per row is
+    // what the walk costs, against 4 bytes here).
+    Index f[GB_PULL_WPI];
+#pragma unroll
+    for (int j = 0; j < GB_PULL_WPI; ++j) {
+      const Index row = (g*GB_PULL_WPI + j)*32 + lane;
+      const bool mbit = (mword[j] >> lane) & 1u;
+      const bool active = (row < nrows) && (UseScmp ? !mbit : mbit);
+      f[j] = static_cast<Index>(-1);
+      if (active) {
+        f[j] = __ldg(first + row);
+        ++inspected;                      // the 4 bytes of first[row]
       }
     }
-    const unsigned int out = __ballot_sync(GB_FULL_MASK, found);
-    if (lane == 0) w_bits[word] = out;
-    if (row < nrows) w[row] = found ? static_cast<W>(1) : static_cast<W>(0);
-    found_total += found ? 1 : 0;
+    unsigned int pword[GB_PULL_WPI];
+#pragma unroll
+    for (int j = 0; j < GB_PULL_WPI; ++j) {
+      pword[j] = 0u;
+      if (f[j] != static_cast<Index>(-1))
+        pword[j] = __ldg(probe + ((f[j] & 0x7fffffff) >> 5));
+    }
+#pragma unroll
+    for (int j = 0; j < GB_PULL_WPI; ++j) {
+      const Index word = g*GB_PULL_WPI + j;
+      const Index row  = word*32 + lane;
+      bool found = (pword[j] >> (f[j] & 31)) & 1u;
+      if (f[j] >= 0 && !(found && UseEarlyExit)) {
+        Index k         = __ldg(rowptr + row) + 1;
+        const Index end = __ldg(rowptr + row + 1);
+        inspected += 2;
+        for (; k < end; ++k) {
+          const Index col = __ldg(colind + k);
+          ++inspected;
+          if ((__ldg(probe + (col >> 5)) >> (col & 31)) & 1u) {
+            found = true;
+            if (UseEarlyExit) break;
+          }
+        }
+      }
+      const unsigned int out = __ballot_sync(GB_FULL_MASK, found);
+      if (word < nwords) {
+        if (lane == 0) w_bits[word] = out;
+        if (row < nrows) w[row] = found ? static_cast<W>(1) : static_cast<W>(0);
+      }
+      found_total += found ? 1 : 0;
+    }
   }
   int total = blockSum<GB_PULL_NT>(found_total, s_red);
   if (threadIdx.x == 0 && total)

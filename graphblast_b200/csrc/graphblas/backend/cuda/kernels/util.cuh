@@ -125,6 +125,36 @@ __global__ void frontierDegreeKernel(Index* __restrict__ deg,
   }
 }
 
+// Single-launch form of frontierDegreeKernel + exclusive scan for short frontiers
+// (the first and last levels of a traversal): offs[i] = sum_{j<i} deg(f[j]) for
+// i in [0, nf], computed by one CTA in chunks of 1024.
+#define GB_DEGSCAN_NT  1024
+#define GB_DEGSCAN_MAX (GB_DEGSCAN_NT*8)
+__global__ void __launch_bounds__(GB_DEGSCAN_NT)
+frontierDegreeScanKernel(Index* __restrict__ offs,
+                         const Index* __restrict__ rowptr,
+                         const Index* __restrict__ f_ind, Index nf) {
+  __shared__ int s_scan[GB_DEGSCAN_NT/32 + 1];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (Index base = 0; base <= nf; base += GB_DEGSCAN_NT) {
+    const Index i = base + threadIdx.x;
+    int d = 0;
+    if (i < nf) {
+      const Index r = f_ind[i];
+      d = rowptr[r+1] - rowptr[r];
+    }
+    int total;
+    const int excl = blockExclusiveScan<GB_DEGSCAN_NT>(d, s_scan, &total);
+    const int carry = s_carry;
+    if (i <= nf) offs[i] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+}
+
 // Binary search helper kept for API parity with reference kernels/util.hpp:8-24.
 __device__ __forceinline__ Index binarySearch(const Index* array, Index target,
                                               Index begin, Index end) {

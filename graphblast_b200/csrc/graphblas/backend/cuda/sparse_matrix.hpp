@@ -141,8 +141,18 @@ class SparseMatrix {
   const Index* spmv_tiles_key_[2];
   Index        spmv_tiles_nvals_[2];
   int          spmv_tiles_count_[2];
+  // Cached "first neighbour" summary of the Boolean pull (same indexing):
+  // entry i = -1 for an empty row, colind[rowptr[i]] for a longer row, and that
+  // value with the top bit set when it is the row's only entry.
+  Index*       d_pull_first_[2];
+  const Index* pull_first_key_[2];
+  Index        pull_first_nvals_[2];
   void dropSpmvTiles() {
     for (int k = 0; k < 2; ++k) {
+      if (d_pull_first_[k] != NULL) gbFree(d_pull_first_[k]);
+      d_pull_first_[k] = NULL;
+      pull_first_key_[k] = NULL;
+      pull_first_nvals_[k] = -1;
       if (d_spmv_tiles_[k] != NULL) gbFree(d_spmv_tiles_[k]);
       d_spmv_tiles_[k] = NULL;
       spmv_tiles_key_[k] = NULL;
@@ -166,6 +176,9 @@ void SparseMatrix<T>::init(Index nrows, Index ncols) {
   symmetric_ = false;
   format_ = getEnv("GRB_SPARSE_MATRIX_FORMAT", GrB_SPARSE_MATRIX_CSRCSC);
   for (int k = 0; k < 2; ++k) {
+    d_pull_first_[k] = NULL;
+    pull_first_key_[k] = NULL;
+    pull_first_nvals_[k] = -1;
     d_spmv_tiles_[k] = NULL;
     spmv_tiles_key_[k] = NULL;
     spmv_tiles_nvals_[k] = -1;
@@ -436,6 +449,7 @@ template <typename T>
 Info SparseMatrix<T>::adoptCsc(Index* col_ptr, Index* row_ind, T* values,
                                bool symmetric) {
   if (d_csrRowPtr_ == NULL) return GrB_UNINITIALIZED_OBJECT;
+  dropSpmvTiles();
   symmetric_ = symmetric;
   if (symmetric && (col_ptr == NULL || row_ind == NULL)) {
     d_cscColPtr_ = d_csrRowPtr_;
@@ -735,6 +749,7 @@ Info SparseMatrix<T>::cpuToGpu() {
     ncapacity_ = nvals_;
   }
   CHECK(allocateGpu());
+  dropSpmvTiles();   // derived caches describe the previous contents
   cudaStream_t s = gbStream();
   const size_t nv = nvals_;
 

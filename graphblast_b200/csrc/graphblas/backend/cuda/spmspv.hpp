@@ -119,11 +119,13 @@ Info spmspvMerge(SparseVector<W>*       w,
   }
 
   const M* mask_val = NULL;
+  const unsigned int* mask_bits = NULL;
   if (use_mask) {
     Storage mask_vec_type;
     CHECK(mask->getStorage(&mask_vec_type));
     if (mask_vec_type == GrB_DENSE) {
       mask_val = mask->dense_.d_val_;
+      if (mask->dense_.bits_valid_) mask_bits = mask->dense_.d_bits_;
     } else if (mask_vec_type == GrB_SPARSE) {
       std::cout << "Spmspv Sparse Mask\n";
       std::cout << "Error: Feature not implemented yet!\n";
@@ -139,15 +141,21 @@ Info spmspvMerge(SparseVector<W>*       w,
   Index* offs = reinterpret_cast<Index*>(desc->scratch(GB_SCRATCH_OFFS,
       2*(static_cast<size_t>(nf) + 1)*sizeof(Index)));
   Index* deg  = offs + (nf + 1);
-  frontierDegreeKernel<<<gridFor(nf + 1, 256), 256, 0, s>>>(deg, A_csrRowPtr,
-      u->d_ind_, nf);
-  GB_KERNEL_CHECK();
-  size_t cub_bytes = 0;
-  CUDA_CALL(cub::DeviceScan::ExclusiveSum(NULL, cub_bytes, deg, offs, nf + 1,
-      s));
-  void* cub_tmp = desc->scratch(GB_SCRATCH_CUB, cub_bytes);
-  CUDA_CALL(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, deg, offs,
-      nf + 1, s));
+  if (nf + 1 <= GB_DEGSCAN_MAX) {
+    frontierDegreeScanKernel<<<1, GB_DEGSCAN_NT, 0, s>>>(offs, A_csrRowPtr,
+        u->d_ind_, nf);
+    GB_KERNEL_CHECK();
+  } else {
+    frontierDegreeKernel<<<gridFor(nf + 1, 256), 256, 0, s>>>(deg, A_csrRowPtr,
+        u->d_ind_, nf);
+    GB_KERNEL_CHECK();
+    size_t cub_bytes = 0;
+    CUDA_CALL(cub::DeviceScan::ExclusiveSum(NULL, cub_bytes, deg, offs, nf + 1,
+        s));
+    void* cub_tmp = desc->scratch(GB_SCRATCH_CUB, cub_bytes);
+    CUDA_CALL(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, deg, offs,
+        nf + 1, s));
+  }
 
   // 2) expand + combine into the accumulator / bitmap.
   unsigned int* bits;
@@ -159,7 +167,7 @@ Info spmspvMerge(SparseVector<W>*       w,
   const int mask_mode = use_mask ? (keep_zero ? 2 : 1) : 0;
 #define GB_LAUNCH_PUSH(SO, MM)                                               \
   spmspvPushKernel<SO, MM><<<grid, GB_PUSH_NT, 0, s>>>(bits, acc, mask_val,  \
-      offs, u->d_ind_, u->d_val_, nf, A_csrRowPtr, A_csrColInd, A_csrVal,    \
+      mask_bits, offs, u->d_ind_, u->d_val_, nf, A_csrRowPtr, A_csrColInd, A_csrVal,    \
       static_cast<W>(op.identity()), extractMul(op), extractAdd(op),      \
       prof_cell)
   unsigned long long* prof_cell = NULL;

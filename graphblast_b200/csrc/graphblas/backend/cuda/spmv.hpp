@@ -146,10 +146,26 @@ Info spmv(DenseVector<W>*        w,
             desc->opreuse() ? mask_bits : u_t->ensureBits();
         unsigned int* w_bits = w->bitsStorage();
         const int grid = gridFor(A_nrows, GB_PULL_NT, 8);
+        // First-neighbour summary of this structure, computed once per matrix.
+        SparseMatrix<a>* A_f = const_cast<SparseMatrix<a>*>(A);
+        const int fw = use_tran ? 1 : 0;
+        if (A_f->d_pull_first_[fw] == NULL ||
+            A_f->pull_first_key_[fw] != A_csrRowPtr ||
+            A_f->pull_first_nvals_[fw] != A->nvals_) {
+          if (A_f->d_pull_first_[fw] != NULL) gbFree(A_f->d_pull_first_[fw]);
+          A_f->d_pull_first_[fw] = reinterpret_cast<Index*>(
+              gbMalloc((static_cast<size_t>(A_nrows) + 1)*sizeof(Index)));
+          pullFirstNeighbourKernel<<<gridFor(A_nrows, 256, 8), 256, 0, s>>>(
+              A_f->d_pull_first_[fw], A_csrRowPtr, A_csrColInd, A_nrows);
+          GB_KERNEL_CHECK();
+          A_f->pull_first_key_[fw]   = A_csrRowPtr;
+          A_f->pull_first_nvals_[fw] = A->nvals_;
+        }
+        const Index* A_first = A_f->d_pull_first_[fw];
 #define GB_LAUNCH_PULL(SC, EE, OR)                                           \
         spmvMaskedOrPullBitsKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(  \
-            w->d_val_, w_bits, mask_bits, u_bits, A_nrows, A_csrRowPtr,      \
-            A_csrColInd, ctr, prof_cell)
+            w->d_val_, w_bits, mask_bits, u_bits, A_nrows, A_first,          \
+            A_csrRowPtr, A_csrColInd, ctr, prof_cell)
         profiler().begin(GB_PROF_PULL_BOOL, s);
         switch (variant) {
           case 0: GB_LAUNCH_PULL(false, false, false); break;
@@ -163,8 +179,9 @@ Info spmv(DenseVector<W>*        w,
           default: break;
         }
 #undef GB_LAUNCH_PULL
-        // rowptr + mask bits + output floats + output bits
-        fixed_bytes = 4.0*(A_nrows + 1) + 4.0*A_nrows + 0.25*A_nrows;
+        // mask bits + output floats + output bits (first-neighbour entries,
+        // rowptr pairs and colind entries are counted where they are read)
+        fixed_bytes = 4.0*A_nrows + 0.25*A_nrows;
       } else {
         const M* mask_val = mask->dense_.d_val_;
         const int grid = gridFor(A_nrows, GB_PULL_NT, 8);

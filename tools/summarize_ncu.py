@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Turns ncu artefacts brought back in gpurun_out/ into the small text summaries
+kept under profiles/.
+
+  summarize_ncu.py launches <launch_list.csv>        per-kernel share table
+  summarize_ncu.py full <capture.ncu-rep>            key metrics per captured launch
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "lts__t_sectors_srcunit_tex_op_read.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_static",
+    "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem",
+    "launch__occupancy_limit_registers",
+]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    h = rows[hi]
+    ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+    agg = collections.OrderedDict()
+    total = 0.0
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        try:
+            ns = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        name = r[ki].split("(")[0].replace("void ", "")
+        name = name.split("<")[0]
+        c = agg.setdefault(name, [0, 0.0])
+        c[0] += 1
+        c[1] += ns
+        total += ns
+    print("# %s: %d launches, %.1f us of kernel time (ncu: cold cache, "
+          "serialised launches; shares only)" % (path, sum(c[0] for c in agg.values()),
+                                                 total / 1e3))
+    print("%-60s %7s %12s %10s %7s" % ("kernel", "count", "total_us", "avg_us", "share"))
+    for name, (cnt, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%-60s %7d %12.1f %10.2f %6.1f%%" % (name[:60], cnt, ns / 1e3,
+                                                   ns / cnt / 1e3, 100 * ns / total))
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    ki = h.index("Kernel Name")
+    print("# %s: %d captured launches (ncu --set full --clock-control none)"
+          % (path, len(rows) - 2))
+    for r in rows[2:]:
+        print("---- " + r[ki][:150])
+        for k in KEYS:
+            if k in h:
+                i = h.index(k)
+                print("  %-78s %16s %s" % (k, r[i], units[i]))
+        if "dram__bytes_read.sum" in h:
+            def val(k):
+                i = h.index(k)
+                v = float(r[i].replace(",", ""))
+                u = units[i]
+                return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0,
+                            "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
+            traffic = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+            t = val("gpu__time_duration.sum")
+            print("  %-78s %16.1f GB/s (dram bytes %.0f)" % (
+                "=> DRAM traffic / duration", traffic / t / 1e9, traffic))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
