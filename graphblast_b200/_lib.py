@@ -90,6 +90,13 @@ SIGNATURES = [
     ("gb200_profile_read", _I, [_I, C.POINTER(_D), C.POINTER(_LL),
                                 C.POINTER(_D)]),
     ("gb200_launch_count", _I, [C.POINTER(_ULL)]),
+    ("gb200_xchg_create", _I, [C.POINTER(_P), _I, _I, C.POINTER(_LL)]),
+    ("gb200_xchg_handle", _I, [_P, _P]),
+    ("gb200_xchg_connect", _I, [_P, _P]),
+    ("gb200_xchg_free", _I, [_P]),
+    ("gb200_xchg_allgather_bits", _I, [_P, _P, C.POINTER(_LL)]),
+    ("gb200_xchg_bits_ptr", _I, [_P, C.POINTER(_P)]),
+    ("gb200_dist_bfs", _I, [_P, _P, _P, _LL, _LL, _P, C.POINTER(_I)]),
 ]
 
 

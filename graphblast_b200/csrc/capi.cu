@@ -634,6 +634,9 @@ int gb200_vector_device_ptr(gb200_vector_t v, void** d_val) {
   graphblas::backend::Vector<float>& b = v->f->vector_;
   if (b.vec_type_ != graphblas::GrB_DENSE)
     return rc(graphblas::GrB_INVALID_OBJECT);
+  graphblas::Info info = b.dense_.allocateGpu();
+  if (info == graphblas::GrB_SUCCESS) info = b.dense_.materialize();
+  if (info != graphblas::GrB_SUCCESS) return rc(info);
   *d_val = b.dense_.d_val_;
   return 0;
 }
@@ -914,10 +917,12 @@ int gb200_vector_import_bits(gb200_vector_t v, const uint32_t* d_bits,
   unsigned int* bits = d.bitsStorage();
   CUDA_CALL(cudaMemcpyAsync(bits, d_bits, d.bitWords()*sizeof(unsigned int),
       cudaMemcpyDeviceToDevice, s));
-  bitmapToDenseKernel<<<gridFor(n, 256), 256, 0, s>>>(d.d_val_, bits, n);
-  GB_KERNEL_CHECK();
+  // values are held lazily: the bitmap is the content until somebody needs
+  // the float array (DenseVector::materialize)
+  (void)n;
   d.touched();
   d.bits_valid_ = true;
+  d.vals_stale_ = true;
   d.zero_one_   = true;
   if (nnz >= 0) {
     d.nnz_          = static_cast<graphblas::Index>(nnz);
@@ -1004,3 +1009,5 @@ int gb200_rmat_edges(int scale, long long nedges, unsigned long long seed,
 }
 
 }  // extern "C"
+
+#include "dist_exchange.cuh"

@@ -21,9 +21,11 @@ Index compactOrdered(Source src, Index nitems, Descriptor* desc) {
   static const bool three_pass = getEnv("GB200_COMPACT_3PASS", 0) != 0;
   if (!three_pass) {
     // one launch, look-back across CTAs (kernels/compact.cuh)
-    unsigned long long* state = desc->lookback(static_cast<size_t>(nblocks) + 1);
+    const int nb1 = static_cast<int>((static_cast<long long>(nitems) +
+        GB_COMPACT_NT*GB_COMPACT_IPT - 1) / (GB_COMPACT_NT*GB_COMPACT_IPT));
+    unsigned long long* state = desc->lookback(static_cast<size_t>(nb1) + 1);
     desc->lookback_epoch_ = desc->lookback_epoch_ % 0x3ffffffeu + 1u;
-    compactOnePassKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems, state,
+    compactOnePassKernel<<<nb1, GB_COMPACT_NT, 0, s>>>(src, nitems, state,
         desc->lookback_epoch_, ctr);
     GB_KERNEL_CHECK();
     return static_cast<Index>(runtime().fetch(ctr));

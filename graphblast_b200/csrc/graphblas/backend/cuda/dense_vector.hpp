@@ -36,13 +36,15 @@ class DenseVector {
       : nvals_(0), nnz_(0), h_val_(NULL), d_val_(NULL), need_update_(0),
         owns_device_(true), nnz_valid_(false), nnz_identity_(T()),
         d_count_(NULL), count_pending_(false), zero_one_(false),
-        d_bits_(NULL), bits_valid_(false), bits_alloc_words_(0) {}
+        d_bits_(NULL), bits_valid_(false), bits_alloc_words_(0),
+        vals_stale_(false) {}
 
   explicit DenseVector(Index nsize)
       : nvals_(nsize), nnz_(0), h_val_(NULL), d_val_(NULL), need_update_(0),
         owns_device_(true), nnz_valid_(false), nnz_identity_(T()),
         d_count_(NULL), count_pending_(false), zero_one_(false),
-        d_bits_(NULL), bits_valid_(false), bits_alloc_words_(0) {}
+        d_bits_(NULL), bits_valid_(false), bits_alloc_words_(0),
+        vals_stale_(false) {}
 
   ~DenseVector();
 
@@ -94,7 +96,26 @@ class DenseVector {
     count_pending_ = false;
     zero_one_ = false;
     bits_valid_ = false;
+    vals_stale_ = false;
   }
+
+  // Lazy values.  The fused Boolean pull publishes its 0/1 result through the
+  // bitmap shadow only and sets vals_stale_; every consumer inside a traversal
+  // (mask of assign, frontier of the next mxv, convert, count) reads the bitmap.
+  // Anything that needs the value array calls materialize() first; anything that
+  // overwrites the whole array clears the flag (touched(), fill(), ...).
+  Info materialize() {
+    if (vals_stale_) {
+      CHECK(allocateGpu());
+      bitmapToDenseKernel<<<gridFor(static_cast<size_t>(nvals_), 256), 256, 0,
+          gbStream()>>>(d_val_, d_bits_, nvals_);
+      GB_KERNEL_CHECK();
+      vals_stale_ = false;
+      need_update_ = true;
+    }
+    return GrB_SUCCESS;
+  }
+  bool vals_stale_;
 
  public:  // (private in the reference; its drivers `#define private public`)
   Index nvals_;  // vector length
@@ -174,6 +195,7 @@ Info DenseVector<T>::nnew(Index nsize) {
   count_pending_ = false;
   zero_one_ = false;
   bits_valid_ = false;
+  vals_stale_ = false;
   return GrB_SUCCESS;
 }
 
@@ -181,6 +203,9 @@ template <typename T>
 Info DenseVector<T>::dup(const DenseVector* rhs) {
   if (nvals_ != rhs->nvals_) CHECK(nnew(rhs->nvals_));
   CHECK(allocateGpu());
+  CHECK(const_cast<DenseVector*>(rhs)->materialize());
+  vals_stale_ = false;
+  bits_valid_ = false;
   if (rhs->d_val_ != NULL && rhs->d_val_ != d_val_)
     CUDA_CALL(cudaMemcpyAsync(d_val_, rhs->d_val_, nvals_*sizeof(T),
         cudaMemcpyDeviceToDevice, gbStream()));
@@ -232,6 +257,7 @@ Info DenseVector<T>::computeNnz(Index* nnz_t, T identity, Descriptor* desc) {
     return GrB_SUCCESS;
   }
   CHECK(allocateGpu());
+  CHECK(materialize());
   unsigned long long* ctr = desc->counters();
   CUDA_CALL(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), gbStream()));
   countNonIdentityKernel<256><<<gridFor(nvals_, 256), 256, 0, gbStream()>>>(
@@ -280,6 +306,7 @@ Info DenseVector<T>::build(T*    values,
   count_pending_ = false;
   zero_one_ = false;
   bits_valid_ = false;
+  vals_stale_ = false;
   return GrB_SUCCESS;
 }
 
@@ -287,6 +314,7 @@ template <typename T>
 Info DenseVector<T>::setElement(T val, Index index) {
   if (index < 0 || index >= nvals_) return GrB_INDEX_OUT_OF_BOUNDS;
   CHECK(allocateGpu());
+  CHECK(materialize());
   T* stage = reinterpret_cast<T*>(runtime().h_pinned);
   runtime().sync();              // staging slot may be in flight
   *stage = val;
@@ -305,6 +333,7 @@ template <typename T>
 Info DenseVector<T>::extractElement(T* val, Index index) {
   if (index < 0 || index >= nvals_) return GrB_INDEX_OUT_OF_BOUNDS;
   CHECK(allocateGpu());
+  CHECK(materialize());
   *val = runtime().fetch(d_val_ + index);
   return GrB_SUCCESS;
 }
@@ -341,6 +370,7 @@ Info DenseVector<T>::extractRaw(T* values, Index n) {
   if (n > nvals_) return GrB_UNINITIALIZED_OBJECT;
   if (n < nvals_) return GrB_INSUFFICIENT_SPACE;
   CHECK(allocateGpu());
+  CHECK(materialize());
   CUDA_CALL(cudaMemcpyAsync(values, d_val_, static_cast<size_t>(n)*sizeof(T),
       cudaMemcpyDeviceToHost, gbStream()));
   runtime().sync();
@@ -363,6 +393,7 @@ Info DenseVector<T>::resize(Index nsize) {
   T* d_old = d_val_;
   bool old_owned = owns_device_;
   Index to_copy = std::min(nsize, nvals_);
+  CHECK(materialize());
   CHECK(gpuToCpu());
   T* h_old = h_val_;
   h_val_ = NULL;
@@ -394,6 +425,7 @@ Info DenseVector<T>::fill(T val) {
   nnz_valid_   = false;
   count_pending_ = false;
   zero_one_ = false;
+  vals_stale_ = false;
   // bitmap shadow of a constant vector: all zero or all one
   CUDA_CALL(cudaMemsetAsync(bitsStorage(), (val != static_cast<T>(0)) ? 0xff : 0,
       bitWords()*sizeof(unsigned int), gbStream()));
@@ -412,6 +444,7 @@ Info DenseVector<T>::fillAscending(Index nvals) {
   count_pending_ = false;
   zero_one_ = false;
   bits_valid_ = false;
+  vals_stale_ = false;
   return GrB_SUCCESS;
 }
 
@@ -472,6 +505,7 @@ Info DenseVector<T>::cpuToGpu() {
   count_pending_ = false;
   zero_one_ = false;
   bits_valid_ = false;
+  vals_stale_ = false;
   return GrB_SUCCESS;
 }
 
@@ -479,6 +513,7 @@ template <typename T>
 Info DenseVector<T>::gpuToCpu(bool force_update) {
   bool fresh_host = (h_val_ == NULL);
   CHECK(allocate());
+  CHECK(materialize());
   if (need_update_ || force_update || fresh_host) {
     CUDA_CALL(cudaMemcpyAsync(h_val_, d_val_,
         static_cast<size_t>(nvals_)*sizeof(T), cudaMemcpyDeviceToHost,
@@ -505,6 +540,7 @@ Info DenseVector<T>::swap(DenseVector* rhs) {  // NOLINT(build/include_what_you_
   std::swap(d_bits_,       rhs->d_bits_);
   std::swap(bits_valid_,   rhs->bits_valid_);
   std::swap(bits_alloc_words_, rhs->bits_alloc_words_);
+  std::swap(vals_stale_,   rhs->vals_stale_);
   return GrB_SUCCESS;
 }
 }  // namespace backend

@@ -75,6 +75,7 @@ compactEmitKernel(Source src, Index nitems,
 // are already running; status words of older launches are recognised by their
 // epoch and never need clearing.
 // ---------------------------------------------------------------------------
+#define GB_COMPACT_IPT  8
 #define GB_LB_AGGREGATE 1ull    // value = this block's own count
 #define GB_LB_INCLUSIVE 2ull    // value = count of blocks 0..b
 
@@ -91,8 +92,17 @@ compactOnePassKernel(Source src, Index nitems,
     s_bid = static_cast<unsigned int>(atomicAdd(state, 1ull));
   __syncthreads();
   const unsigned int bid = s_bid;
-  const Index item = static_cast<Index>(bid)*GB_COMPACT_NT + threadIdx.x;
-  const int c = (item < nitems) ? src.count(item) : 0;
+  // GB_COMPACT_IPT consecutive items per thread (blocked, so order is kept): the
+  // look-back chain is as long as the grid, so CTAs are made coarse.
+  const Index item0 = (static_cast<Index>(bid)*GB_COMPACT_NT + threadIdx.x)
+                      *GB_COMPACT_IPT;
+  int cnt[GB_COMPACT_IPT];
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < GB_COMPACT_IPT; ++j) {
+    cnt[j] = (item0 + j < nitems) ? src.count(item0 + j) : 0;
+    c += cnt[j];
+  }
   int total;
   const int excl = blockExclusiveScan<GB_COMPACT_NT>(c, s_scan, &total);
 
@@ -135,8 +145,12 @@ compactOnePassKernel(Source src, Index nitems,
     }
   }
   __syncthreads();
-  if (c > 0) src.emit(item, s_prefix + excl);
-  else if (item < nitems) src.finish(item);
+  int pos = s_prefix + excl;
+#pragma unroll
+  for (int j = 0; j < GB_COMPACT_IPT; ++j) {
+    if (cnt[j] > 0) { src.emit(item0 + j, pos); pos += cnt[j]; }
+    else if (item0 + j < nitems) src.finish(item0 + j);
+  }
 
   // last CTA out resets the two counters for the next launch
   if (threadIdx.x == 0) {

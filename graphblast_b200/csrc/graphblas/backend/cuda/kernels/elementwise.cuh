@@ -208,19 +208,30 @@ template <bool UseScmp, typename U>
 __global__ void assignDenseBitsMaskKernel(U* u, unsigned int* u_bits, Index n,
                                           const unsigned int* mask_bits,
                                           U val) {
+  // Each lane fetches one mask word (one coalesced 128-byte request covers 1024
+  // rows); the warp then walks the non-empty words, so the stores of different
+  // words are not separated by a dependent load.
   const int lane = threadIdx.x & 31;
-  Index word = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+  const Index warp   = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
   const Index nwarps = (gridDim.x*blockDim.x) >> 5;
   const Index nwords = (n + 31) >> 5;
-  for (; word < nwords; word += nwarps) {
-    unsigned int sel = __ldg(mask_bits + word);
-    if (UseScmp) sel = ~sel;
-    const Index base = word*32;
-    if (base + 32 > n) sel &= (n - base >= 32) ? 0xffffffffu
-                                                : ((1u << (n - base)) - 1u);
-    if (sel == 0u) continue;
-    if ((sel >> lane) & 1u) u[base + lane] = val;
-    if (u_bits != NULL && lane == 0) {
+  for (Index wbase = warp*32; wbase < nwords; wbase += nwarps*32) {
+    const Index word = wbase + lane;
+    unsigned int sel = 0u;
+    if (word < nwords) {
+      sel = __ldg(mask_bits + word);
+      if (UseScmp) sel = ~sel;
+      const Index base = word*32;
+      if (base + 32 > n) sel &= (1u << (n - base)) - 1u;
+    }
+    unsigned int pending = __ballot_sync(GB_FULL_MASK, sel != 0u);
+    while (pending) {
+      const int j = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const unsigned int s = __shfl_sync(GB_FULL_MASK, sel, j);
+      if ((s >> lane) & 1u) u[(wbase + j)*32 + lane] = val;
+    }
+    if (u_bits != NULL && sel != 0u) {
       if (val != static_cast<U>(0)) u_bits[word] |= sel;
       else                          u_bits[word] &= ~sel;
     }

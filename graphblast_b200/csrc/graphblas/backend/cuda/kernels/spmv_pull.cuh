@@ -425,7 +425,9 @@ spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
       const unsigned int out = __ballot_sync(GB_FULL_MASK, found);
       if (word < nwords) {
         if (lane == 0) w_bits[word] = out;
-        if (row < nrows) w[row] = found ? static_cast<W>(1) : static_cast<W>(0);
+        // w == NULL: the caller holds the values lazily (bitmap only)
+        if (w != NULL && row < nrows)
+          w[row] = found ? static_cast<W>(1) : static_cast<W>(0);
       }
       found_total += found ? 1 : 0;
     }

@@ -208,6 +208,10 @@ Info eWiseMult(Vector<W>*       w,
                const Vector<V>* v,
                Descriptor*      desc) {
   Vector<V>* v_t = const_cast<Vector<V>*>(v);
+  CHECK(u->materialize());
+  CHECK(v->materialize());
+  CHECK(w->materialize());
+  if (mask != NULL) CHECK(mask->materialize());
 
   Storage u_vec_type;
   Storage v_vec_type;
@@ -309,6 +313,7 @@ Info eWiseMult(Matrix<c>*       C,
   CHECK(desc->get(GrB_INP0, &inp0_mode));
   CHECK(desc->get(GrB_INP1, &inp1_mode));
   if (inp0_mode != GrB_DEFAULT) return GrB_INVALID_VALUE;
+  CHECK(B->materialize());
 
   Storage A_mat_type;
   Storage B_vec_type;
@@ -351,6 +356,10 @@ Info eWiseAdd(Vector<W>*       w,
               Descriptor*      desc) {
   Vector<U>* u_t = const_cast<Vector<U>*>(u);
   Vector<V>* v_t = const_cast<Vector<V>*>(v);
+  CHECK(u->materialize());
+  CHECK(v->materialize());
+  CHECK(w->materialize());
+  if (mask != NULL) CHECK(mask->materialize());
 
   Storage u_vec_type;
   Storage v_vec_type;
@@ -411,6 +420,8 @@ Info eWiseAdd(Vector<W>*       w,
               const Vector<U>* u,
               V                val,
               Descriptor*      desc) {
+  CHECK(u->materialize());
+  CHECK(w->materialize());
   Storage u_vec_type;
   CHECK(u->getStorage(&u_vec_type));
   if (u_vec_type != GrB_DENSE && u_vec_type != GrB_SPARSE)
@@ -471,6 +482,11 @@ Info assign(Vector<W>*           w,
 
   Storage vec_type;
   CHECK(w->getStorage(&vec_type));
+  // The target is written in part; a dense mask is read through its bitmap
+  // shadow when that is current (which lazily held values imply), except by the
+  // sparse-target filter, which reads mask values.
+  CHECK(w->materialize());
+  if (vec_type == GrB_SPARSE && mask != NULL) CHECK(mask->materialize());
 
   if (vec_type == GrB_SPARSE) {
     CHECK(assignSparse(&w->sparse_, mask, accum, val, indices, nindices,
@@ -496,6 +512,9 @@ Info apply(Vector<W>*       w,
            const Vector<U>* u,
            Descriptor*      desc) {
   Vector<U>* u_t = const_cast<Vector<U>*>(u);
+  CHECK(u->materialize());
+  CHECK(w->materialize());
+  if (mask != NULL) CHECK(mask->materialize());
   Storage u_vec_type;
   CHECK(u->getStorage(&u_vec_type));
   if (u_vec_type == GrB_SPARSE) {

@@ -59,6 +59,7 @@ Info reduceInner(T*                     val,
     *val = static_cast<T>(count);
     return GrB_SUCCESS;
   }
+  CHECK(u_t->materialize());
   return reduceCommon(val, accum, op, u->d_val_, u->nvals_, desc);
 }
 

@@ -137,6 +137,7 @@ Info spmv(DenseVector<W>*        w,
       // assign() and this kernel itself, so inside a BFS no conversion pass runs;
       // a stale shadow costs one 4n-byte pass here.
       const bool bits_form = (op.identity() == static_cast<U>(0));
+      bool lazy_vals = false;
       double fixed_bytes;
       if (bits_form) {
         DenseVector<M>* mask_dense =
@@ -162,9 +163,14 @@ Info spmv(DenseVector<W>*        w,
           A_f->pull_first_nvals_[fw] = A->nvals_;
         }
         const Index* A_first = A_f->d_pull_first_[fw];
+        // The 0/1 result is published through the bitmap shadow only; the value
+        // array is written when somebody asks for it (DenseVector::materialize).
+        static const bool eager = getEnv("GB200_EAGER_VALUES", 0) != 0;
+        W* w_out = eager ? w->d_val_ : static_cast<W*>(NULL);
+        lazy_vals = !eager;
 #define GB_LAUNCH_PULL(SC, EE, OR)                                           \
         spmvMaskedOrPullBitsKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(  \
-            w->d_val_, w_bits, mask_bits, u_bits, A_nrows, A_first,          \
+            w_out, w_bits, mask_bits, u_bits, A_nrows, A_first,              \
             A_csrRowPtr, A_csrColInd, ctr, prof_cell)
         profiler().begin(GB_PROF_PULL_BOOL, s);
         switch (variant) {
@@ -179,10 +185,12 @@ Info spmv(DenseVector<W>*        w,
           default: break;
         }
 #undef GB_LAUNCH_PULL
-        // mask bits + output floats + output bits (first-neighbour entries,
+        // mask bits + output bits [+ output floats] (first-neighbour entries,
         // rowptr pairs and colind entries are counted where they are read)
-        fixed_bytes = 4.0*A_nrows + 0.25*A_nrows;
+        fixed_bytes = (eager ? 4.0*A_nrows : 0.0) + 0.25*A_nrows;
       } else {
+        CHECK(mask->materialize());
+        CHECK(u_t->materialize());
         const M* mask_val = mask->dense_.d_val_;
         const int grid = gridFor(A_nrows, GB_PULL_NT, 8);
 #define GB_LAUNCH_PULL(SC, EE, OR)                                           \
@@ -209,13 +217,14 @@ Info spmv(DenseVector<W>*        w,
       profiler().end(GB_PROF_PULL_BOOL, s, fixed_bytes);
       w->touched();
       w->bits_valid_ = bits_form;
+      w->vals_stale_ = lazy_vals;
       // The kernel wrote 0/1 and counted the ones: the next convert() or
       // a PlusMonoid reduce can reuse the count (one 8-byte read, no pass).
       w->count_pending_ = true;
       w->zero_one_      = true;
       w->nnz_identity_  = static_cast<W>(0);
       if (desc->debug())
-        printDevice("w_val", w->d_val_, A_nrows);
+        { w->materialize(); printDevice("w_val", w->d_val_, A_nrows); }
     } else if (mask_vec_type == GrB_SPARSE) {
       std::cout << "DeVec Sparse Mask logical_or Spmv\n";
       std::cout << "Error: Feature not implemented yet!\n";
@@ -223,6 +232,9 @@ Info spmv(DenseVector<W>*        w,
       return GrB_UNINITIALIZED_OBJECT;
     }
   } else {
+    CHECK(u_t->materialize());
+    if (use_mask) CHECK(mask->materialize());
+    if (use_accum) CHECK(w->materialize());
     W* w_val;
     if (use_accum)
       w_val = reinterpret_cast<W*>(desc->scratch(GB_SCRATCH_VEC_A,

@@ -83,6 +83,15 @@ class Vector {
   Storage         vec_type_;
 
   float           ratio_;  // nnz/size seen at the previous convert()
+
+  // Writes out lazily held values of a dense vector (dense_vector.hpp).
+  Info materialize() {
+    if (vec_type_ == GrB_DENSE) return dense_.materialize();
+    return GrB_SUCCESS;
+  }
+  Info materialize() const {
+    return const_cast<Vector*>(this)->materialize();
+  }
 };
 
 template <typename T>
@@ -354,6 +363,12 @@ Info Vector<T>::dense2sparse(T identity, Descriptor* desc) {
 
   LoadBalanceMode mxv_mode = getEnv("GRB_LOAD_BALANCE_MODE",
       GrB_LOAD_BALANCE_MERGE);
+
+  // Lazy values are only tolerable on the structure-only bitmap path below.
+  if (dense_.vals_stale_ &&
+      !(identity == static_cast<T>(0) && desc->struconly() &&
+        mxv_mode == GrB_LOAD_BALANCE_MERGE))
+    CHECK(dense_.materialize());
 
   Index count;
   if (dense_.bits_valid_ && identity == static_cast<T>(0)) {

@@ -145,6 +145,54 @@ class Comm(object):
         return self.gbits, total
 
 
+class PeerExchange(object):
+    """The library's own exchange (include/graphblast_b200.h, gb200_xchg_*): every
+    rank maps every other rank's exchange block through CUDA IPC; the owner's
+    kernel stores its frontier slice, count and epoch flag into all peers over
+    NVLink, and the level loop runs in C++ (gb200_dist_bfs).  torch.distributed
+    is used once, to pass the 64-byte IPC handles around."""
+
+    def __init__(self, gb, comm, device):
+        import torch.distributed as dist
+        self.lib = gb._lib.load()
+        self.world, self.rank = comm.world, comm.rank
+        for p in range(self.world + 1):
+            assert comm.bounds[p] % 32 == 0 or p == self.world
+        offs = (C.c_longlong * (self.world + 1))(*comm.offsets)
+        self._h = C.c_void_p()
+        rc = self.lib.gb200_xchg_create(C.byref(self._h), self.world, self.rank,
+                                        offs)
+        if rc != 0:
+            raise RuntimeError("gb200_xchg_create failed: %d" % rc)
+        mine = (C.c_ubyte * 64)()
+        rc = self.lib.gb200_xchg_handle(self._h, mine)
+        if rc != 0:
+            raise RuntimeError("gb200_xchg_handle failed: %d" % rc)
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+        allh = torch.zeros(64 * self.world, dtype=torch.uint8, device=device)
+        if self.world > 1:
+            dist.all_gather_into_tensor(allh, t)
+        else:
+            allh.copy_(t)
+        buf = allh.cpu().numpy().tobytes()
+        rc = self.lib.gb200_xchg_connect(self._h, buf)
+        if rc != 0:
+            raise RuntimeError("gb200_xchg_connect failed: %d" % rc)
+
+    def bfs(self, ops, n, source):
+        levels = C.c_int(0)
+        rc = self.lib.gb200_dist_bfs(self._h, ops.v._h, ops.M._h, n, source,
+                                     ops.desc._h, C.byref(levels))
+        if rc != 0:
+            raise RuntimeError("gb200_dist_bfs failed: %d" % rc)
+        return levels.value
+
+    def close(self):
+        if self._h:
+            self.lib.gb200_xchg_free(self._h)
+            self._h = C.c_void_p()
+
+
 # ---------------------------------------------------------------------------
 # Local operations through the C ABI (GPU)
 # ---------------------------------------------------------------------------
@@ -255,6 +303,7 @@ def run_bfs(ops, comm, source, max_levels=10000):
 def bench_distributed(args, world, rank, local_rank):
     """bench.py body for WORLD_SIZE > 1: strong scaling of the headline BFS."""
     import os
+    import sys
     import time
     import torch.distributed as dist
     import graphblast_b200 as gb
@@ -286,8 +335,35 @@ def bench_distributed(args, world, rank, local_rank):
     ops = GpuLocalOps(gb, n, lo, hi, rp_l, ci_l, colptr, rowind, desc)
     comm = Comm(bounds, dev)
 
+    # Exchange: the library's peer-memory path unless it cannot be set up (no
+    # IPC / peer access) or GB200_DIST_EXCHANGE=nccl asks for the NCCL baseline.
+    xchg = None
+    why = "requested"
+    if os.environ.get("GB200_DIST_EXCHANGE", "peer") == "peer":
+        try:
+            xchg = PeerExchange(gb, comm, dev)
+        except Exception as e:               # noqa: BLE001
+            why = str(e)
+            xchg = None
+    agree = torch.tensor([1 if xchg is not None else 0], device=dev)
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+    if int(agree.item()) == 0:
+        if xchg is not None:
+            xchg.close()
+        xchg = None
+        if rank == 0:
+            print("peer exchange unavailable (%s): NCCL all-gather path" % why,
+                  file=sys.stderr)
+
+    def traverse():
+        if xchg is not None:
+            return xchg.bfs(ops, n, source)
+        return run_bfs(ops, comm, source)
+
+    torch.cuda.synchronize()
+    dist.barrier()
     for _ in range(max(args.warmup, 1)):
-        run_bfs(ops, comm, source)
+        traverse()
     torch.cuda.synchronize()
     dist.barrier()
 
@@ -302,7 +378,7 @@ def bench_distributed(args, world, rank, local_rank):
     ev0.record()
     levels = 0
     for _ in range(args.steps):
-        levels = run_bfs(ops, comm, source)
+        levels = traverse()
     ev1.record()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -358,9 +434,17 @@ def bench_distributed(args, world, rank, local_rank):
             "n": n, "nnz": nnz, "source": source, "levels": levels,
             "partition": "1-D nnz-balanced row slices, bounds %s" % bounds,
             "nnz_per_rank": [int(g.item()) for g in gathered],
-            "exchange": "NCCL all-gather of the frontier bitmap "
-                        "(%d bytes per level) + counts" % (4 * comm.rec * world),
-            "flags": "--mxvmode 0 --struconly 1 --earlyexit 1 (opreuse off: the "
+            "exchange": ("peer-memory stores of the owned frontier slice into "
+                         "every rank's replica (CUDA IPC over NVLink), flag + "
+                         "count per level, level loop in C++"
+                         if xchg is not None else
+                         "NCCL all-gather of the frontier bitmap (%d bytes per "
+                         "level) + counts, level loop in Python"
+                         % (4 * comm.rec * world)),
+            "flags": "--struconly 1 --earlyexit 1; pull levels probe the "
+                     "replicated cumulative visited bitmap (global operand reuse)"
+                     if xchg is not None else
+                     "--mxvmode 0 --struconly 1 --earlyexit 1 (opreuse off: the "
                      "visited mask is local)",
             "l2_policy": "inputs larger than L2"},
         "e2e": {"value": nnz / (float(ms[1].item()) / args.steps * 1e3),

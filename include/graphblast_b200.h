@@ -232,6 +232,35 @@ int gb200_launch_count(unsigned long long* out);
 int gb200_rmat_edges(int scale, long long nedges, unsigned long long seed,
                      long long first_edge, int* d_src, int* d_dst);
 
+/* ---- Multi-GPU: frontier exchange over peer memory ----------
+ * One process per GPU.  Each rank creates an exchange over the same partition of
+ * the replicated bitmap (word_offsets[world+1], in 32-bit words; rank r owns words
+ * [word_offsets[r], word_offsets[r+1])), passes its 64-byte IPC handle to every
+ * other rank by any host channel (torch.distributed, MPI, a file), and connects.
+ * After that the exchange needs no host library: the owner's kernel stores its
+ * slice, count and epoch flag directly into every peer's copy over NVLink.
+ * The reference has no multi-GPU code; this is the frontier all-gather that
+ * BASELINE.json's north_star asks for after each mxv. */
+typedef struct gb200_xchg_s* gb200_xchg_t;
+int gb200_xchg_create(gb200_xchg_t* out, int world, int rank,
+                      const long long* word_offsets);
+int gb200_xchg_handle(gb200_xchg_t x, void* out64);
+int gb200_xchg_connect(gb200_xchg_t x, const void* handles /* world x 64 bytes */);
+int gb200_xchg_free(gb200_xchg_t x);
+/* Publishes the owned slice (vector of the owned length, dense or sparse) and
+ * waits for all ranks; *total_out = global number of entries. */
+int gb200_xchg_allgather_bits(gb200_xchg_t x, gb200_vector_t v,
+                              long long* total_out);
+/* DEVICE pointer to the replicated bitmap of the last completed exchange. */
+int gb200_xchg_bits_ptr(gb200_xchg_t x, const uint32_t** d_bits);
+/* Level-synchronous BFS over the 1-D row partition with the level loop in the
+ * library: v = levels of the owned vertices (length = owned rows of M), M = the
+ * owned rows of A^T as an (owned x n) matrix with CSR and CSC.  Collective: every
+ * rank calls it with the same n and source. */
+int gb200_dist_bfs(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
+                   long long n, long long source, gb200_desc_t desc,
+                   int* levels_out);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus
