@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace graphblas {
 namespace backend {
@@ -164,6 +165,58 @@ __device__ __forceinline__ void atomicCombine(T* addr, T val, AddOp add_op) {
     if (next_bits == old) return;
     unsigned int prev = atomicCAS(a, old, next_bits);
     if (prev == old) return;
+    old = prev;
+  }
+}
+
+// Same combine, returning the cell's value BEFORE this update.  `kind` is what
+// the semiring's add answers for add(3, 5) — the reference's own way of telling
+// monoids apart (spmv.hpp:76-85): 3 = minimum, 5 = maximum, 8 = plus.  For float
+// cells those three map to one native atomic (ordered-int trick for min/max:
+// non-negative floats order like signed ints, negative floats like reversed
+// unsigned ints); everything else takes the CAS loop.
+template <typename T, typename AddOp>
+__device__ __forceinline__ T atomicCombineFetch(T* addr, T val, AddOp add_op,
+                                                int kind) {
+  static_assert(sizeof(T) == 4, "atomicCombineFetch handles 32-bit values");
+  if (std::is_same<T, float>::value && (kind == 3 || kind == 5 || kind == 8)) {
+    float* fa = reinterpret_cast<float*>(addr);
+    float fv;
+    memcpy(&fv, &val, 4);
+    float old;
+    if (kind == 8) {
+      old = atomicAdd(fa, fv);
+    } else {
+      const bool as_signed = (kind == 3) ? (fv >= 0.f) : (fv < 0.f);
+      if (kind == 3) {
+        old = as_signed
+            ? __int_as_float(atomicMin(reinterpret_cast<int*>(fa),
+                                       __float_as_int(fv)))
+            : __uint_as_float(atomicMax(reinterpret_cast<unsigned int*>(fa),
+                                        __float_as_uint(fv)));
+      } else {
+        old = !as_signed
+            ? __int_as_float(atomicMax(reinterpret_cast<int*>(fa),
+                                       __float_as_int(fv)))
+            : __uint_as_float(atomicMin(reinterpret_cast<unsigned int*>(fa),
+                                        __float_as_uint(fv)));
+      }
+    }
+    T out;
+    memcpy(&out, &old, 4);
+    return out;
+  }
+  unsigned int* a = reinterpret_cast<unsigned int*>(addr);
+  unsigned int old = *a;
+  while (true) {
+    T cur;
+    memcpy(&cur, &old, 4);
+    T next = add_op(cur, val);
+    unsigned int next_bits;
+    memcpy(&next_bits, &next, 4);
+    if (next_bits == old) return cur;
+    unsigned int prev = atomicCAS(a, old, next_bits);
+    if (prev == old) return cur;
     old = prev;
   }
 }

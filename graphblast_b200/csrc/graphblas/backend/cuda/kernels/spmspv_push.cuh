@@ -53,6 +53,7 @@ spmspvPushKernel(unsigned int* __restrict__ bits,
                  W                          identity,
                  MulOp                      mul_op,
                  AddOp                      add_op,
+                 int                        add_kind,  // add_op(3, 5)
                  unsigned long long*        edge_bytes) {
   __shared__ Index s_offs[GB_PUSH_SEG + 1];
   __shared__ Index s_base[GB_PUSH_SEG];
@@ -133,9 +134,23 @@ spmspvPushKernel(unsigned int* __restrict__ bits,
             W prod;
             if (av == identity || uv == identity) prod = identity;
             else                                  prod = mul_op(av, uv);
-            atomicCombine(acc + col, prod, add_op);
+            // min / max: a cell that already absorbs this product needs no
+            // atomic at all — and no bit either, whoever moved it off the
+            // identity has set that.  (The plain load may be stale; for a
+            // monotone cell that only makes the filter weaker.)
+            bool absorbed = false;
+            if (add_kind == 3 || add_kind == 5) {
+              const W cur = acc[col];
+              absorbed = (cur != identity) && (add_op(cur, prod) == cur);
+            }
+            if (!absorbed) {
+              // the touched bit is set by the update that finds the identity
+              const W old = atomicCombineFetch(acc + col, prod, add_op, add_kind);
+              if (old == identity) bitSetAtomic(bits, col);
+            }
+          } else {
+            bitSetAtomic(bits, col);
           }
-          bitSetAtomic(bits, col);
         }
       }
     }

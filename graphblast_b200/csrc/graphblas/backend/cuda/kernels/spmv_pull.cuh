@@ -64,7 +64,7 @@ __global__ void spmvMergePartitionKernel(Index* __restrict__ tile_rows,
   tile_rows[c] = mergePathRows(d, rowptr, nrows, nnz);
 }
 
-template <int NT, int IPT, bool Vec256, bool Gather,
+template <int NT, int IPT, bool Vec256, bool Gather, bool LaneMajor,
           typename W, typename a, typename U,
           typename MulOp, typename AddOp>
 __global__ void __launch_bounds__(NT)
@@ -109,6 +109,40 @@ spmvMergeKernelT(W* __restrict__           w,
   // Products mul(A(k), u[col(k)]) for k in [k0, k1) go to s_prod[k - k0a].
   const uint64_t pol = makeEvictLastPolicy();
   const int nchunks = (nk > 0) ? ((k1 - k0a + 7) >> 3) : 0;
+  if (LaneMajor) {
+    // Lanes of a warp take CONSECUTIVE nonzeros (32-bit loads, 128 bytes per
+    // instruction, same bytes per wavefront as the 256-bit form): one gather
+    // instruction then covers 32 neighbouring entries of (usually) one row, whose
+    // sorted column indices fall into far fewer 128-byte lines than 32 entries
+    // taken 8 apart, and the product stores are conflict free.  The L1 data pipe
+    // (wavefronts), not HBM, is what this kernel saturates.
+    const int span = (nk > 0) ? (k1 - k0a) : 0;
+    for (int g = wid*256; g < span; g += (NT/32)*256) {
+      Index col[8];
+      a     av[8];
+      U     uv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const Index k = k0a + g + j*32 + lane;
+        col[j] = (k >= k0 && k < k1) ? ldStream(colind + k)
+                                     : static_cast<Index>(-1);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const Index k = k0a + g + j*32 + lane;
+        if (col[j] >= 0) av[j] = ldStream(val + k);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (col[j] >= 0) uv[j] = ldGather(u + col[j], pol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int p = g + j*32 + lane;
+        if (p < span)
+          s_prod[p] = (col[j] >= 0) ? mul_op(av[j], uv[j]) : identity;
+      }
+    }
+  } else
   for (int c = t; c < nchunks; c += NT) {
     const Index kb = k0a + (c << 3);
     W prods[8];

@@ -169,7 +169,8 @@ Info spmspvMerge(SparseVector<W>*       w,
   spmspvPushKernel<SO, MM><<<grid, GB_PUSH_NT, 0, s>>>(bits, acc, mask_val,  \
       mask_bits, offs, u->d_ind_, u->d_val_, nf, A_csrRowPtr, A_csrColInd, A_csrVal,    \
       static_cast<W>(op.identity()), extractMul(op), extractAdd(op),      \
-      prof_cell)
+      add_kind, prof_cell)
+  const int add_kind = static_cast<int>(extractAdd(op)(3, 5));
   unsigned long long* prof_cell = NULL;
   if (profiler().enabled) {
     profiler().ensureCells();

@@ -48,12 +48,17 @@ Info spmvMergeLaunch(W*           out,
       sizeof(a) == 4 && sizeof(Index) == 4;
   const double alg_bytes = 8.0*nnz + 12.0*nrows + 4.0;
   profiler().begin(GB_PROF_SPMV_MERGE, s);
-  if (aligned)
-    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, true><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
+  static const int load_mode = getEnv("GB200_SPMV_LOADS", 2);
+  if (load_mode == 2 && sizeof(a) == 4)
+    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true, true><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
+        carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
+        extractMul(op), extractAdd(op));
+  else if (aligned)
+    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, true, false><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
         extractMul(op), extractAdd(op));
   else
-    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
+    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true, false><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
         extractMul(op), extractAdd(op));
   GB_KERNEL_CHECK();

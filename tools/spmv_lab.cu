@@ -112,7 +112,7 @@ float runMerge(float* w, const int* rowptr, const int* colind, const float* val,
   thrust::device_vector<float> cval(nctas);
   spmvMergePartitionKernel<<<(nctas + 256)/256, 256>>>(
       thrust::raw_pointer_cast(tiles.data()), rowptr, n, nnz, nctas, tile);
-  auto kern = spmvMergeKernelT<NT, IPT, true, Gather, float, float, float,
+  auto kern = spmvMergeKernelT<NT, IPT, true, Gather, false, float, float, float,
       decltype(graphblas::extractMul(op)), decltype(graphblas::extractAdd(op))>;
   if (carveout >= 0)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
