@@ -36,6 +36,8 @@ struct gb200_xchg_s {
   graphblas::Vector<float>* f_own;
   graphblas::Vector<float>* f2;
   graphblas::Vector<float>* f_glob;
+  // vectors of the PageRank loop: p_glob, p_prev_own, p_swap, r, r_temp
+  graphblas::Vector<float>* pr_vec[5];
 };
 
 namespace gbx {
@@ -52,7 +54,8 @@ xchgPublishKernel(const unsigned int* __restrict__ src, size_t nwords,
                   size_t word_lo, char* const* __restrict__ peers, int world,
                   int rank, size_t off_data, size_t off_counts, size_t off_flags,
                   unsigned long long epoch, unsigned long long* d_cells,
-                  const unsigned long long* d_count_in) {
+                  const unsigned long long* d_count_in, int use_imm,
+                  unsigned long long imm) {
   __shared__ int s_red[GBX_NT/32];
   int pop = 0;
   size_t i = static_cast<size_t>(blockIdx.x)*GBX_NT + threadIdx.x;
@@ -67,7 +70,7 @@ xchgPublishKernel(const unsigned int* __restrict__ src, size_t nwords,
     }
   }
   const int total = blockSum<GBX_NT>(pop, s_red);
-  if (threadIdx.x == 0 && total != 0 && d_count_in == NULL)
+  if (threadIdx.x == 0 && total != 0 && d_count_in == NULL && !use_imm)
     atomicAdd(d_cells + 1, static_cast<unsigned long long>(total));
   __threadfence_system();          // this CTA's peer stores before its "done"
   __syncthreads();
@@ -75,7 +78,7 @@ xchgPublishKernel(const unsigned int* __restrict__ src, size_t nwords,
     const unsigned long long done = atomicAdd(d_cells, 1ull);
     if (done == gridDim.x - 1) {
       __threadfence();
-      const unsigned long long cnt = (d_count_in != NULL)
+      const unsigned long long cnt = use_imm ? imm : (d_count_in != NULL)
           ? *d_count_in
           : *reinterpret_cast<volatile unsigned long long*>(d_cells + 1);
       for (int p = 0; p < world; ++p) {
@@ -101,7 +104,7 @@ __global__ void xchgWaitKernel(const char* __restrict__ local, size_t off_counts
                                size_t off_flags, int world,
                                unsigned long long epoch,
                                unsigned long long* d_cells,
-                               long long timeout_cycles) {
+                               long long timeout_cycles, int as_double) {
   const int lane = threadIdx.x;
   bool ok = true;
   if (lane < world) {
@@ -119,6 +122,19 @@ __global__ void xchgWaitKernel(const char* __restrict__ local, size_t off_counts
   if (ok && lane < world)
     c = *(reinterpret_cast<const volatile unsigned long long*>(
         local + off_counts) + lane);
+  if (as_double) {
+    // the per-rank cells hold doubles (partial sums); lane 0 adds them in rank
+    // order so every rank computes the identical total
+    double sum = 0.0;
+    for (int p = 0; p < world; ++p) {
+      const unsigned long long bits = __shfl_sync(GB_FULL_MASK, c, p);
+      sum += __longlong_as_double(static_cast<long long>(bits));
+    }
+    if (lane == 0)
+      d_cells[2] = ok ? static_cast<unsigned long long>(
+          __double_as_longlong(sum)) : ~0ull;
+    return;
+  }
   for (int d = 16; d > 0; d >>= 1)
     c += __shfl_down_sync(GB_FULL_MASK, c, d);
   if (lane == 0) d_cells[2] = ok ? c : ~0ull;
@@ -137,7 +153,8 @@ __global__ void setBitKernel(unsigned int* words, long long bit) {
 }
 
 inline int publish(gb200_xchg_s* x, const unsigned int* d_words,
-                   const unsigned long long* d_count) {
+                   const unsigned long long* d_count, int use_imm = 0,
+                   unsigned long long imm = 0ull) {
   cudaStream_t s = gbStream();
   x->epoch += 1;
   const int par = static_cast<int>(x->epoch & 1ull);
@@ -147,20 +164,26 @@ inline int publish(gb200_xchg_s* x, const unsigned int* d_words,
   if (grid < 1) grid = 1;
   xchgPublishKernel<<<grid, GBX_NT, 0, s>>>(d_words, nw, x->word_off[x->rank],
       x->d_peer, x->world, x->rank, x->off_data[par], x->off_counts[par],
-      x->off_flags, x->epoch, x->d_cells, d_count);
+      x->off_flags, x->epoch, x->d_cells, d_count, use_imm, imm);
   GB_KERNEL_CHECK();
   return 0;
 }
 
-// Returns the global count of the epoch just published, or -1 on timeout.
-inline long long wait(gb200_xchg_s* x) {
+// Waits for the epoch just published; returns the raw 8-byte total (integer
+// sum of the ranks' cells, or the bits of their double sum), ~0 on timeout.
+inline unsigned long long waitRaw(gb200_xchg_s* x, int as_double) {
   cudaStream_t s = gbStream();
   const int par = static_cast<int>(x->epoch & 1ull);
   // ~10 s at 2 GHz: a rank that died must not hang the others' GPUs
   xchgWaitKernel<<<1, 32, 0, s>>>(x->local, x->off_counts[par], x->off_flags,
-      x->world, x->epoch, x->d_cells, 20000000000ll);
+      x->world, x->epoch, x->d_cells, 20000000000ll, as_double);
   GB_KERNEL_CHECK();
-  const unsigned long long total = runtime().fetch(x->d_cells + 2);
+  return runtime().fetch(x->d_cells + 2);
+}
+
+// Returns the global count of the epoch just published, or -1 on timeout.
+inline long long wait(gb200_xchg_s* x) {
+  const unsigned long long total = waitRaw(x, 0);
   if (total == ~0ull) return -1;
   return static_cast<long long>(total);
 }
@@ -207,6 +230,7 @@ int gb200_xchg_create(gb200_xchg_t* out, int world, int rank,
     CUDA_CALL(cudaMemcpy(x->d_peer, x->peer.data(), sizeof(char*),
         cudaMemcpyHostToDevice));
   x->f_own = NULL; x->f2 = NULL; x->f_glob = NULL;
+  for (int i = 0; i < 5; ++i) x->pr_vec[i] = NULL;
   *out = x;
   return 0;
 }
@@ -251,6 +275,7 @@ int gb200_xchg_free(gb200_xchg_t x) {
   cudaFree(x->local); cudaFree(x->d_cells); cudaFree(x->d_visited);
   cudaFree(x->d_seed); cudaFree(x->d_peer);
   delete x->f_own; delete x->f2; delete x->f_glob;
+  for (int i = 0; i < 5; ++i) delete x->pr_vec[i];
   delete x;
   return 0;
 }
@@ -368,13 +393,104 @@ int gb200_dist_bfs(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
         LogicalOrAndSemiring<float>(), M->f, x->f_glob, d);
     CHECK(d->toggle(GrB_MASK));
     if (info != GrB_SUCCESS) break;
-    if (gb200_vector_export_bits_async(&f2_h, x->d_seed, x->d_cells + 3) != 0) { info = GrB_PANIC; break; }
-    gbx::publish(x, x->d_seed, x->d_cells + 3);
+    // the publish kernel counts the bits it sends
+    if (gb200_vector_export_bits(&f2_h, x->d_seed, NULL) != 0) { info = GrB_PANIC; break; }
+    gbx::publish(x, x->d_seed, NULL);
     total = gbx::wait(x);
     if (total < 0) { info = GrB_PANIC; break; }
   }
   d->set(GrB_MXVMODE, saved_mode);
   if (levels_out != NULL) *levels_out = level;
+  return rc(info);
+}
+
+// Generic form for 32-bit payloads (float vectors): publishes nwords_owned words
+// from d_words with this rank's partial scalar; *sum_out = sum over ranks.
+int gb200_xchg_allgather_words(gb200_xchg_t x, const void* d_words,
+                               double partial, double* sum_out) {
+  if (x == NULL || d_words == NULL || sum_out == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  if (!x->connected) return rc(graphblas::GrB_UNINITIALIZED_OBJECT);
+  GB200_REQUIRE_DEVICE();
+  unsigned long long bits;
+  memcpy(&bits, &partial, 8);
+  gbx::publish(x, static_cast<const unsigned int*>(d_words), NULL, 1, bits);
+  const unsigned long long total = gbx::waitRaw(x, 1);
+  if (total == ~0ull) return rc(graphblas::GrB_PANIC);
+  memcpy(sum_out, &total, 8);
+  return 0;
+}
+
+// PageRank over the 1-D row partition (the loop of algorithm/pr.hpp on the owned
+// slice).  The exchange must have been created with one word per VERTEX
+// (word_offsets = vertex bounds).  p (length nl) = owned ranks (output);
+// M = owned rows of (alpha * A ./ outdeg)^T as an (nl x n) CSR matrix.
+// Per iteration: p_swap = M (+.x) p_glob ; p = p_swap + (1-alpha)/n ;
+// r = p - p_prev ; err_partial = sum(r.*r) ; peers exchange p and the partial.
+int gb200_dist_pr(gb200_xchg_t x, gb200_vector_t p, gb200_matrix_t M,
+                  long long n, float alpha, float eps, gb200_desc_t desc,
+                  int* iters_out) {
+  if (x == NULL || p == NULL || M == NULL || desc == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  if (!x->connected || M->f == NULL) return rc(graphblas::GrB_UNINITIALIZED_OBJECT);
+  GB200_REQUIRE_DEVICE();
+  using namespace graphblas;          // NOLINT(build/namespaces)
+  Descriptor* d = &desc->desc;
+  const size_t lo = x->word_off[x->rank];
+  Index nl;
+  CHECK(p->f->size(&nl));
+  if (static_cast<size_t>(nl) != x->word_off[x->rank + 1] - lo ||
+      x->total_words != static_cast<size_t>(n))
+    return rc(GrB_DIMENSION_MISMATCH);
+  if (x->pr_vec[0] == NULL) {
+    x->pr_vec[0] = new Vector<float>(static_cast<Index>(n));   // p_glob (view)
+    x->pr_vec[1] = new Vector<float>(nl);                      // p_prev (view)
+    for (int i = 2; i < 5; ++i) x->pr_vec[i] = new Vector<float>(nl);
+  }
+  Vector<float>* p_glob = x->pr_vec[0];
+  Vector<float>* p_prev = x->pr_vec[1];
+  Vector<float>* p_swap = x->pr_vec[2];
+  Vector<float>* r      = x->pr_vec[3];
+  Vector<float>* r_temp = x->pr_vec[4];
+
+  CHECK(p->f->fill(1.f/static_cast<float>(n)));
+  void* p_dev = NULL;
+  if (gb200_vector_device_ptr(p, &p_dev) != 0) return rc(GrB_PANIC);
+  double total = 0.0;
+  int info_i = gb200_xchg_allgather_words(x, p_dev, 0.0, &total);
+  if (info_i != 0) return info_i;
+
+  Desc_value saved_mode;
+  CHECK(d->get(GrB_MXVMODE, &saved_mode));
+  CHECK(d->set(GrB_MXVMODE, GrB_PULLONLY));
+  const int max_niter = d->descriptor_.max_niter_;
+  float error = 1.f;
+  int iter;
+  Info info = GrB_SUCCESS;
+  for (iter = 1; error > eps && iter <= max_niter; ++iter) {
+    float* data = const_cast<float*>(
+        reinterpret_cast<const float*>(gbx::current(x)));
+    info = p_glob->build(data, static_cast<Index>(n));          if (info) break;
+    info = p_prev->build(data + lo, nl);                        if (info) break;
+    info = mxv<float, float, float, float>(p_swap, GrB_NULL, GrB_NULL,
+        PlusMultipliesSemiring<float>(), M->f, p_glob, d);      if (info) break;
+    info = eWiseAdd<float, float, float, float>(p->f, GrB_NULL, GrB_NULL,
+        PlusMultipliesSemiring<float>(), p_swap,
+        (1.f - alpha)/static_cast<float>(n), d);                if (info) break;
+    info = eWiseMult<float, float, float, float>(r, GrB_NULL, GrB_NULL,
+        PlusMinusSemiring<float>(), p->f, p_prev, d);           if (info) break;
+    info = eWiseAdd<float, float, float, float>(r_temp, GrB_NULL, GrB_NULL,
+        MultipliesMultipliesSemiring<float>(), r, r, d);        if (info) break;
+    float partial = 0.f;
+    info = reduce<float, float>(&partial, GrB_NULL, PlusMonoid<float>(), r_temp,
+        d);                                                     if (info) break;
+    if (gb200_vector_device_ptr(p, &p_dev) != 0) { info = GrB_PANIC; break; }
+    if (gb200_xchg_allgather_words(x, p_dev, static_cast<double>(partial),
+                                   &total) != 0) { info = GrB_PANIC; break; }
+    error = static_cast<float>(sqrt(total));
+  }
+  d->set(GrB_MXVMODE, saved_mode);
+  if (iters_out != NULL) *iters_out = iter - 1;
   return rc(info);
 }
 

@@ -152,13 +152,18 @@ class PeerExchange(object):
     NVLink, and the level loop runs in C++ (gb200_dist_bfs).  torch.distributed
     is used once, to pass the 64-byte IPC handles around."""
 
-    def __init__(self, gb, comm, device):
+    def __init__(self, gb, comm, device, offsets=None):
+        """offsets: partition of the replicated array in 32-bit words; default =
+        the bitmap partition (one bit per vertex), pass the vertex bounds for
+        float payloads (one word per vertex)."""
         import torch.distributed as dist
         self.lib = gb._lib.load()
         self.world, self.rank = comm.world, comm.rank
         for p in range(self.world + 1):
             assert comm.bounds[p] % 32 == 0 or p == self.world
-        offs = (C.c_longlong * (self.world + 1))(*comm.offsets)
+        if offsets is None:
+            offsets = comm.offsets
+        offs = (C.c_longlong * (self.world + 1))(*[int(o) for o in offsets])
         self._h = C.c_void_p()
         rc = self.lib.gb200_xchg_create(C.byref(self._h), self.world, self.rank,
                                         offs)
@@ -186,6 +191,14 @@ class PeerExchange(object):
         if rc != 0:
             raise RuntimeError("gb200_dist_bfs failed: %d" % rc)
         return levels.value
+
+    def pr(self, p_own, M, n, alpha, eps, desc):
+        iters = C.c_int(0)
+        rc = self.lib.gb200_dist_pr(self._h, p_own._h, M._h, n, alpha, eps,
+                                    desc._h, C.byref(iters))
+        if rc != 0:
+            raise RuntimeError("gb200_dist_pr failed: %d" % rc)
+        return iters.value
 
     def close(self):
         if self._h:
@@ -301,7 +314,12 @@ def run_bfs(ops, comm, source, max_levels=10000):
 
 
 def bench_distributed(args, world, rank, local_rank):
-    """bench.py body for WORLD_SIZE > 1: strong scaling of the headline BFS."""
+    """bench.py body for WORLD_SIZE > 1: strong scaling of the headline BFS
+    (--algo pr: of PageRank, BASELINE.json configs[3])."""
+    if args.algo == "pr":
+        return bench_distributed_pr(args, world, rank, local_rank)
+    if args.algo != "bfs":
+        raise SystemExit("--algo %s has no multi-GPU path yet (bfs, pr)" % args.algo)
     import os
     import sys
     import time
@@ -456,5 +474,157 @@ def bench_distributed(args, world, rank, local_rank):
         "cpu_baseline": cpu_baseline,
         "parity_vs_cpu_reference": parity,
     }
+    dist.destroy_process_group()
+    return result
+
+
+def bench_distributed_pr(args, world, rank, local_rank):
+    """PageRank (10 power iterations) over the 1-D row partition: local merge-path
+    SpMV on the owned rows, p exchanged through peer memory after every mxv."""
+    import os
+    import sys
+    import time
+    import torch.distributed as dist
+    import graphblast_b200 as gb
+    from graphblast_b200 import graphs
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    alpha, niter = 0.85, 10
+    n = 1 << args.scale
+    src, dst = graphs.rmat_edges(args.scale, args.edgefactor, seed=args.seed,
+                                 device=dev)
+    rowptr, colind = graphs.build_csr(n, src, dst, undirected=True)
+    del src, dst
+    nnz = int(colind.numel())
+    deg = (rowptr[1:] - rowptr[:-1]).to(torch.float32)
+    bounds = partition_bounds(rowptr, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    nl = hi - lo
+    e0, e1 = int(rowptr[lo]), int(rowptr[hi])
+    rp_l = (rowptr[lo:hi + 1] - rowptr[lo]).to(torch.int32).contiguous()
+    ci_l = colind[e0:e1].contiguous()
+    # (alpha * A ./ outdeg)^T restricted to the owned rows: entry (i, j) = alpha/deg(j)
+    val_l = (alpha / deg[ci_l.to(torch.int64)]).contiguous()
+    h_rowptr = rowptr.cpu().numpy() if rank == 0 else None
+    h_colind = colind.cpu().numpy() if rank == 0 else None
+    del rowptr, colind, deg
+    torch.cuda.empty_cache()
+
+    lib = gb._lib.load()
+    M = gb.Matrix(max(nl, 1), n)
+    M._keep = [rp_l, ci_l, val_l]
+    rc = lib.gb200_matrix_adopt_csr(M._h, C.c_void_p(rp_l.data_ptr()),
+                                    C.c_void_p(ci_l.data_ptr()),
+                                    C.c_void_p(val_l.data_ptr()), int(ci_l.numel()))
+    assert rc == 0, rc
+    p_own = gb.Vector(max(nl, 1))
+    desc = gb.Descriptor(mxvmode=0, max_niter=niter)
+    comm = Comm(bounds, dev)
+    xchg = PeerExchange(gb, comm, dev, offsets=bounds)
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    for _ in range(max(args.warmup, 1)):
+        xchg.pr(p_own, M, n, alpha, 0.0, desc)
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches0 = C.c_ulonglong(0)
+    lib.gb200_launch_count(C.byref(launches0))
+    lib.gb200_profile_enable(1)
+    lib.gb200_profile_reset()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    iters = 0
+    for _ in range(args.steps):
+        iters = xchg.pr(p_own, M, n, alpha, 0.0, desc)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1), wall_ms], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches1 = C.c_ulonglong(0)
+    lib.gb200_launch_count(C.byref(launches1))
+    ms_per_step = float(ms[0].item()) / args.steps
+    # merge-kernel time on this rank (CUDA events inside the library)
+    k_ms, k_n, k_b = C.c_double(0), C.c_longlong(0), C.c_double(0)
+    lib.gb200_profile_read(0, C.byref(k_ms), C.byref(k_n), C.byref(k_b))
+    kern = torch.tensor([k_ms.value / max(k_n.value, 1),
+                         k_b.value / max(k_n.value, 1)], device=dev,
+                        dtype=torch.float64)
+    kern_all = [torch.zeros_like(kern) for _ in range(world)]
+    dist.all_gather(kern_all, kern)
+
+    mine = torch.from_numpy(p_own.extractTuples()[:nl].astype(np.float32)).to(dev)
+    sizes = [bounds[q + 1] - bounds[q] for q in range(world)]
+    pad = max(sizes)
+    buf = torch.zeros(pad, dtype=torch.float32, device=dev)
+    buf[:mine.numel()] = mine
+    allv = torch.zeros(pad * world, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(allv, buf)
+    parity = None
+    max_rel = None
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
+            os.path.abspath(__file__))), "tests"))
+        import oracle_binding as orc
+        got = np.concatenate([allv[q * pad:q * pad + sizes[q]].cpu().numpy()
+                              for q in range(world)])
+        kind = "reference" if orc.ref() is not None else "port"
+        fn = orc.ref_pr if kind == "reference" else orc.pr
+        t0 = time.perf_counter()
+        want = fn(h_rowptr, h_colind, alpha, 0.0, niter)
+        dt = time.perf_counter() - t0
+        max_rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)))
+        parity = bool(max_rel <= 1e-5)
+        cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS", "cores": 1,
+                        "kind": kind, "ms": dt * 1e3,
+                        "host_cores_total": os.cpu_count(),
+                        "sample": "one full PageRank (10 iterations) of the same graph"}
+    from json import loads
+    peak = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(
+                os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
+            peak = float(loads(f.read()).get("hbm_gbs"))
+    except Exception:                        # noqa: BLE001
+        peak = 7700.0
+    slow = max(float(k[0].item()) for k in kern_all)
+    ach = max(float(k[1].item()) for k in kern_all) / (slow * 1e-3) / 1e9 if slow > 0 else 0.0
+    result = {
+        "metric": "MTEPS", "value": nnz / (ms_per_step * 1e3),
+        "unit": "MTEPS (stored entries of A / time of one PageRank run x 1e-6)",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": "PageRank (PlusMultiplies mxv, %d iterations) on R-MAT "
+                        "scale-%d ef-%d seed %d, symmetrised"
+                        % (niter, args.scale, args.edgefactor, args.seed),
+            "n": n, "nnz": nnz, "iterations": iters,
+            "partition": "1-D nnz-balanced row slices, bounds %s" % bounds,
+            "exchange": "peer-memory stores of the owned float slice into every "
+                        "rank's replica (CUDA IPC over NVLink) + residual partial "
+                        "per iteration, loop in C++",
+            "l2_policy": "inputs larger than L2"},
+        "e2e": {"value": nnz / (float(ms[1].item()) / args.steps * 1e3),
+                "unit": "MTEPS", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 8 * niter,
+                "note": "host wall clock around the same K steps (max over ranks)"},
+        "gpu_launches": int(launches1.value - launches0.value),
+        "roofline": {"kernel": "spmvMergeKernel (merge-path pull SpMV), slowest rank",
+                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak if peak else None, "traffic": None,
+                     "ms_per_launch": slow},
+        "cpu_baseline": cpu_baseline,
+        "parity_vs_cpu_reference": parity,
+        "max_rel_err": max_rel,
+    }
+    xchg.close()
     dist.destroy_process_group()
     return result

@@ -261,6 +261,21 @@ int gb200_dist_bfs(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
                    long long n, long long source, gb200_desc_t desc,
                    int* levels_out);
 
+/* Same exchange for 32-bit payloads (float vectors: create the exchange with one
+ * word per vertex).  Publishes the owned words from DEVICE memory together with
+ * this rank's partial scalar; *sum_out = the ranks' partials added in rank order
+ * (identical on every rank). */
+int gb200_xchg_allgather_words(gb200_xchg_t x, const void* d_words,
+                               double partial, double* sum_out);
+/* PageRank over the 1-D row partition: the loop of reference
+ * graphblas/algorithm/pr.hpp:50-84 on the owned slice, p exchanged through peer
+ * memory after every mxv.  p = owned ranks (length = owned rows of M); M = owned
+ * rows of (alpha * A ./ outdeg)^T, (owned x n), CSR.  Runs until the global
+ * residual norm <= eps or desc max_niter iterations. */
+int gb200_dist_pr(gb200_xchg_t x, gb200_vector_t p, gb200_matrix_t M,
+                  long long n, float alpha, float eps, gb200_desc_t desc,
+                  int* iters_out);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

@@ -82,3 +82,58 @@ def test_two_ranks_peer_exchange():
     assert res["n_gpus"] == 2
     assert res["parity_vs_cpu_reference"] is True
     assert "peer-memory" in res["config"]["exchange"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [10, 15])
+def test_native_pagerank_world1(scale):
+    """gb200_dist_pr on one rank (the owner publishes into its own replica) against
+    the oracle: 10 power iterations, 1e-5 relative."""
+    import ctypes as C
+    import graphblast_b200 as gb
+    from graphblast_b200 import dist as gdist
+    dev = torch.device("cuda", 0)
+    rp, ci = orc.rmat_csr(scale)
+    n = len(rp) - 1
+    alpha = 0.85
+    rowptr = torch.from_numpy(rp).to(dev)
+    colind = torch.from_numpy(ci).to(dev)
+    deg = (rowptr[1:] - rowptr[:-1]).to(torch.float32)
+    val = (alpha / deg[colind.to(torch.int64)]).contiguous()
+    lib = gb._lib.load()
+    M = gb.Matrix(n, n)
+    assert lib.gb200_matrix_adopt_csr(M._h, C.c_void_p(rowptr.data_ptr()),
+                                      C.c_void_p(colind.data_ptr()),
+                                      C.c_void_p(val.data_ptr()), int(len(ci))) == 0
+    p = gb.Vector(n)
+    desc = gb.Descriptor(mxvmode=0, max_niter=10)
+    comm = gdist.Comm([0, n], dev)
+    x = gdist.PeerExchange(gb, comm, dev, offsets=[0, n])
+    try:
+        for _ in range(2):
+            iters = x.pr(p, M, n, alpha, 0.0, desc)
+            assert iters == 10
+            got = p.extractTuples()[:n]
+            want = orc.pr(rp, ci, alpha, 0.0, 10)
+            rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+            assert rel.max() <= 1e-5
+    finally:
+        x.close()
+
+
+@pytest.mark.gpu
+def test_two_ranks_pagerank():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, GB200_BENCH_SCALE="18")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "bench.py"),
+           "--gpus", "2", "--algo", "pr", "--steps", "2", "--warmup", "1"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    res = json.loads(lines[0])
+    assert res["n_gpus"] == 2
+    assert res["parity_vs_cpu_reference"] is True, res["max_rel_err"]
