@@ -18,8 +18,12 @@ Index compactOrdered(Source src, Index nitems, Descriptor* desc) {
       (static_cast<long long>(nitems) + GB_COMPACT_NT - 1) / GB_COMPACT_NT);
   unsigned long long* ctr = desc->counters() + 1;
   cudaStream_t s = gbStream();
-  static const bool three_pass = getEnv("GB200_COMPACT_3PASS", 0) != 0;
-  if (!three_pass) {
+  // The single-launch look-back form is opt-in: measured on B200 it ties the
+  // three-launch form on the sparse BFS frontiers (0.567 vs 0.554 ms per RMAT-24
+  // traversal) and loses badly on dense SSSP frontiers, where its coarse CTAs
+  // serialise the emit loops (408 us per launch at RMAT-24).
+  static const bool one_pass = getEnv("GB200_COMPACT_1PASS", 0) != 0;
+  if (one_pass) {
     // one launch, look-back across CTAs (kernels/compact.cuh)
     const int nb1 = static_cast<int>((static_cast<long long>(nitems) +
         GB_COMPACT_NT*GB_COMPACT_IPT - 1) / (GB_COMPACT_NT*GB_COMPACT_IPT));

@@ -139,11 +139,19 @@ spmspvPushKernel(unsigned int* __restrict__ bits,
             // identity has set that.  (The plain load may be stale; for a
             // monotone cell that only makes the filter weaker.)
             bool absorbed = false;
+            bool touched_before = false;
             if (add_kind == 3 || add_kind == 5) {
               const W cur = acc[col];
-              absorbed = (cur != identity) && (add_op(cur, prod) == cur);
+              touched_before = (cur != identity);
+              absorbed = touched_before && (add_op(cur, prod) == cur);
             }
-            if (!absorbed) {
+            if (absorbed) {
+              // nothing to do
+            } else if (touched_before) {
+              // the cell left the identity earlier (its bit is set or about to
+              // be): result unused, so this compiles to a fire-and-forget RED
+              (void)atomicCombineFetch(acc + col, prod, add_op, add_kind);
+            } else {
               // the touched bit is set by the update that finds the identity
               const W old = atomicCombineFetch(acc + col, prod, add_op, add_kind);
               if (old == identity) bitSetAtomic(bits, col);
