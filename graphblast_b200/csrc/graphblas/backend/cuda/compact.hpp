@@ -36,10 +36,9 @@ Index compactOrdered(Source src, Index nitems, Descriptor* desc) {
   }
   int* block_counts = reinterpret_cast<int*>(
       desc->scratch(GB_SCRATCH_BLOCKSUM, static_cast<size_t>(nblocks)*sizeof(int)));
-  compactCountKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
-      block_counts);
-  GB_KERNEL_CHECK();
-  compactScanKernel<<<1, 1024, 0, s>>>(block_counts, nblocks, ctr);
+  // count + (last CTA) scan of the per-CTA counts, then emit: two launches
+  compactCountScanKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
+      block_counts, nblocks, desc->counters() + 2, ctr);
   GB_KERNEL_CHECK();
   compactEmitKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
       block_counts);

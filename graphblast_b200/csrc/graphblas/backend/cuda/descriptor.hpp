@@ -129,10 +129,17 @@ class Descriptor {
   unsigned int       lookback_epoch_;
   unsigned long long lookback_ticket_;
 
-  // Device counters: 64 x 8-byte cells.
+  // Device counters: 64 x 8-byte cells, zero when first handed out.  Cell 2 is
+  // the "finished CTAs" counter of the compaction's count pass, which leaves it
+  // at zero again.
   unsigned long long* counters() {
+    if (slot_ptr_[GB_SCRATCH_COUNTERS] == NULL) {
+      void* p = scratch(GB_SCRATCH_COUNTERS, 64*sizeof(unsigned long long));
+      CUDA_CALL(cudaMemsetAsync(p, 0, slot_size_[GB_SCRATCH_COUNTERS],
+          gbStream()));
+    }
     return reinterpret_cast<unsigned long long*>(
-        scratch(GB_SCRATCH_COUNTERS, 64*sizeof(unsigned long long)));
+        slot_ptr_[GB_SCRATCH_COUNTERS]);
   }
 
  public:  // (private in the reference; its drivers `#define private public`)

@@ -30,6 +30,47 @@ compactCountKernel(Source src, Index nitems, int* __restrict__ block_counts) {
   if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
 }
 
+// Count pass with the scan folded in: the CTA that finishes last (a counter that
+// it leaves at zero again) scans the per-CTA counts in place, so the ordered
+// compaction is two launches.
+template <typename Source>
+__global__ void __launch_bounds__(GB_COMPACT_NT)
+compactCountScanKernel(Source src, Index nitems, int* __restrict__ block_counts,
+                       int nblocks, unsigned long long* __restrict__ done,
+                       unsigned long long* __restrict__ total_out) {
+  __shared__ int s_scan[GB_COMPACT_NT/32 + 1];
+  __shared__ int s_carry;
+  __shared__ bool s_last;
+  Index item = static_cast<Index>(blockIdx.x)*GB_COMPACT_NT + threadIdx.x;
+  int c = (item < nitems) ? src.count(item) : 0;
+  int total = blockSum<GB_COMPACT_NT>(c, s_scan);
+  if (threadIdx.x == 0) {
+    block_counts[blockIdx.x] = total;
+    __threadfence();
+    s_last = (atomicAdd(done, 1ull) == gridDim.x - 1);
+    s_carry = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  volatile int* counts = block_counts;
+  for (int base = 0; base < nblocks; base += GB_COMPACT_NT) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nblocks) ? counts[i] : 0;
+    int chunk_total;
+    const int excl = blockExclusiveScan<GB_COMPACT_NT>(v, s_scan, &chunk_total);
+    const int carry = s_carry;
+    if (i < nblocks) counts[i] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *total_out = static_cast<unsigned long long>(s_carry);
+    *done = 0ull;
+  }
+}
+
 // Single CTA: in-place exclusive scan of block_counts[0..nblocks), total to
 // *total_out (64-bit cell).
 __global__ void __launch_bounds__(1024)
