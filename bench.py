@@ -126,6 +126,19 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(args, kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
+    kernel, from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json, written by tools/summarize_ncu.py traffic); None when
+    no capture of this (algo, scale, kernel) has been taken."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        table = json.load(open(path))
+        return table.get("%s:%d:%d" % (args.algo, args.scale, kind))
+    except Exception:
+        return None
+
+
 def build_graph(args, torch, gb, graphs):
     """R-MAT on the device with the reference loader's semantics (undirected,
     no self-loops, no duplicates, sorted rows)."""
@@ -349,7 +362,7 @@ def main():
         "bytes_per_launch": dom_bytes / dom_launches if dom_launches else 0,
         "ms_per_launch": dom_ms / dom_launches if dom_launches else 0,
         "share_of_step": dom_ms / total_ms if total_ms else 0,
-        "traffic": None,
+        "traffic": measured_traffic(args, dom),
         "all_kernels": {kinds[k]: {"ms": prof[k][0], "launches": prof[k][1],
                                    "alg_bytes": prof[k][2]} for k in range(4)},
     }

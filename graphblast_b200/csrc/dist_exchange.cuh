@@ -60,13 +60,30 @@ xchgPublishKernel(const unsigned int* __restrict__ src, size_t nwords,
   int pop = 0;
   size_t i = static_cast<size_t>(blockIdx.x)*GBX_NT + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x)*GBX_NT;
-  for (; i < nwords; i += stride) {
-    const unsigned int w = src[i];
-    pop += __popc(w);
-    for (int p = 0; p < world; ++p) {
-      unsigned int* dst =
-          reinterpret_cast<unsigned int*>(peers[p] + off_data) + word_lo + i;
-      *dst = w;
+  const bool vec = ((nwords | word_lo) & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (vec) {
+    // 16-byte loads and peer stores (the float payloads are megabytes per rank)
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    const size_t n4 = nwords >> 2;
+    for (; i < n4; i += stride) {
+      const uint4 w = src4[i];
+      pop += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+      for (int p = 0; p < world; ++p) {
+        uint4* dst = reinterpret_cast<uint4*>(
+            reinterpret_cast<unsigned int*>(peers[p] + off_data) + word_lo) + i;
+        *dst = w;
+      }
+    }
+  } else {
+    for (; i < nwords; i += stride) {
+      const unsigned int w = src[i];
+      pop += __popc(w);
+      for (int p = 0; p < world; ++p) {
+        unsigned int* dst =
+            reinterpret_cast<unsigned int*>(peers[p] + off_data) + word_lo + i;
+        *dst = w;
+      }
     }
   }
   const int total = blockSum<GBX_NT>(pop, s_red);
@@ -159,8 +176,8 @@ inline int publish(gb200_xchg_s* x, const unsigned int* d_words,
   x->epoch += 1;
   const int par = static_cast<int>(x->epoch & 1ull);
   const size_t nw = x->word_off[x->rank + 1] - x->word_off[x->rank];
-  int grid = static_cast<int>((nw + GBX_NT - 1)/GBX_NT);
-  if (grid > 2*runtime().sm_count) grid = 2*runtime().sm_count;
+  int grid = static_cast<int>((nw/4 + GBX_NT - 1)/GBX_NT);
+  if (grid > 4*runtime().sm_count) grid = 4*runtime().sm_count;
   if (grid < 1) grid = 1;
   xchgPublishKernel<<<grid, GBX_NT, 0, s>>>(d_words, nw, x->word_off[x->rank],
       x->d_peer, x->world, x->rank, x->off_data[par], x->off_counts[par],

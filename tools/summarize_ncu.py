@@ -87,5 +87,38 @@ def full(path):
                 "=> DRAM traffic / duration", traffic / t / 1e9, traffic))
 
 
+def traffic(path, key, name_filter):
+    """Average DRAM bytes (read + write) per captured launch whose kernel name
+    contains name_filter -> profiles/traffic.json[key] (key = algo:scale:kind)."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    ki = h.index("Kernel Name")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    vals = []
+    for r in rows[2:]:
+        if name_filter not in r[ki]:
+            continue
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(k)
+            tot += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+        vals.append(tot)
+    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "profiles", "traffic.json")
+    table = json.load(open(dst)) if os.path.exists(dst) else {}
+    table[key] = sum(vals) / len(vals)
+    table[key + ":source"] = "%s (%d launches of %s)" % (
+        os.path.basename(path), len(vals), name_filter)
+    json.dump(table, open(dst, "w"), indent=1, sort_keys=True)
+    print(key, table[key], len(vals))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
