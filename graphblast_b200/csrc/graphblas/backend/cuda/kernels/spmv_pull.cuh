@@ -26,8 +26,16 @@ namespace graphblas {
 namespace backend {
 
 #define GB_SPMV_NT   128
-#define GB_SPMV_IPT  7                               // merge items per thread
+#define GB_SPMV_IPT  9                               // merge items per thread
+// Share of the SM's 256 KB given to shared memory.  The kernel needs ~4.7 KB per
+// CTA; everything else should be L1, which is what holds the loads in flight and
+// the hot part of the gathered vector (tools/spmv_lab.cu sweep, RMAT-22:
+// 25 % -> 0.49 ms, 50 % -> 0.60 ms, 100 % -> 1.33 ms).
+#define GB_SPMV_CARVEOUT 25
 #define GB_SPMV_TILE (GB_SPMV_NT*GB_SPMV_IPT)        // merge items per CTA
+// Resident CTAs per SM the register allocation must allow: full occupancy (2048
+// threads).  Without the cap ptxas takes 40+ registers and the kernel loses 20 %.
+#define GB_SPMV_MINB(NT) ((2048/(NT)) > 32 ? 32 : (2048/(NT)))
 
 // Merge-path split: on diagonal d (d = rows consumed + nonzeros consumed) return
 // the number of row-end items consumed.  List A is row_end[r] = rowptr[r+1],
@@ -74,7 +82,7 @@ __device__ __forceinline__ int prodSlot(int p) { return p ^ ((p >> 3) & 4); }
 template <int NT, int IPT, bool Vec256, bool Gather, bool LaneMajor,
           typename W, typename a, typename U,
           typename MulOp, typename AddOp>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, GB_SPMV_MINB(NT))
 spmvMergeKernelT(W* __restrict__           w,
                 const Index* __restrict__ tile_rows,
                 Index* __restrict__       carry_row,
@@ -88,9 +96,16 @@ spmvMergeKernelT(W* __restrict__           w,
                 W                         identity,
                 MulOp                     mul_op,
                 AddOp                     add_op) {
-  __shared__ Index s_rowend[(NT*IPT) + 1];
-  __shared__ __align__(32) W s_prod[(NT*IPT) + 16];
-  __shared__ W     s_out[(NT*IPT)];
+  // One buffer: products grow from the bottom, row ends from the top.  A tile has
+  // nr row ends and nk nonzeros with nr + nk <= NT*IPT, the product window adds at
+  // most 14 slots of alignment slack and the row ends one entry (the open row).
+  // Keeping the footprint at ~3.7 KB per CTA matters more than anything else in
+  // this kernel: L1 capacity is what bounds the loads in flight (B200, RMAT-22:
+  // 0.54 ms with a 50 % shared-memory carve-out, 0.72 ms at 75 %, 1.33 ms at 100 %).
+  static_assert(sizeof(W) == 4 && sizeof(Index) == 4, "32-bit values and indices");
+  __shared__ __align__(32) unsigned int s_buf[(NT*IPT) + 40];
+  W* const s_prod = reinterpret_cast<W*>(s_buf);
+#define GB_S_ROWEND(i) (reinterpret_cast<Index*>(s_buf)[(NT*IPT) + 39 - (i)])
   __shared__ Index s_wkey[NT/32];
   __shared__ W     s_wval[NT/32];
 
@@ -195,7 +210,7 @@ spmvMergeKernelT(W* __restrict__           w,
   // ---- phase 1b: row-end offsets for rows r0 .. r1 (last = still-open row) ----
   for (int i = t; i <= nr; i += NT) {
     const Index r = r0 + i;
-    s_rowend[i] = (r < nrows) ? __ldg(rowptr + r + 1) : nnz;
+    GB_S_ROWEND(i) = (r < nrows) ? __ldg(rowptr + r + 1) : nnz;
   }
   __syncthreads();
 
@@ -213,7 +228,7 @@ spmvMergeKernelT(W* __restrict__           w,
     int lo = 0, hi = nr;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (mid + (s_rowend[mid] - k0) < target) lo = mid + 1; else hi = mid;
+      if (mid + (GB_S_ROWEND(mid) - k0) < target) lo = mid + 1; else hi = mid;
     }
     start_i = lo;
   }
@@ -227,7 +242,8 @@ spmvMergeKernelT(W* __restrict__           w,
   Index k = k0 + (ld - i);            // global nonzero index
   const int first_i = i;
   W acc = identity;
-  Index rowend = s_rowend[i];
+  W head_val = identity;              // first row that ends in this thread's range
+  Index rowend = GB_S_ROWEND(i);
 #pragma unroll
   for (int it = 0; it < IPT; ++it) {
     if (it < nit) {
@@ -235,10 +251,12 @@ spmvMergeKernelT(W* __restrict__           w,
         acc = add_op(acc, s_prod[prodSlot(k - k0a)]);
         ++k;
       } else {
-        s_out[i] = acc;
+        // A finished row goes straight to global memory (neighbouring threads
+        // finish neighbouring rows); only the first one waits for the carry-in.
+        if (i == first_i) head_val = acc; else w[r0 + i] = acc;
         acc = identity;
         ++i;
-        rowend = s_rowend[i];
+        rowend = GB_S_ROWEND(i);
       }
     }
   }
@@ -277,16 +295,14 @@ spmvMergeKernelT(W* __restrict__           w,
     if (ekey == key0 && ck == ekey) carry_in = add_op(cv, eval);
   }
 
-  if (i > first_i) s_out[first_i] = add_op(carry_in, s_out[first_i]);
+  if (i > first_i) w[r0 + first_i] = add_op(carry_in, head_val);
 
   if (t == NT - 1) {
     W out = (i > first_i) ? acc : add_op(carry_in, acc);
     carry_row[blockIdx.x] = (r0 + i < nrows) ? (r0 + i) : -1;
     carry_val[blockIdx.x] = out;
   }
-  __syncthreads();
-
-  for (int j = t; j < nr; j += NT) w[r0 + j] = s_out[j];
+#undef GB_S_ROWEND
 }
 
 // One thread per CTA carry: the first carry of a run of equal rows folds the

@@ -48,8 +48,22 @@ Info spmvMergeLaunch(W*           out,
       sizeof(a) == 4 && sizeof(Index) == 4;
   const double alg_bytes = 8.0*nnz + 12.0*nrows + 4.0;
   profiler().begin(GB_PROF_SPMV_MERGE, s);
-  static const int load_mode = getEnv("GB200_SPMV_LOADS", 2);
-  if (load_mode == 2 && sizeof(a) == 4)
+  typedef decltype(extractMul(op)) MulT;
+  typedef decltype(extractAdd(op)) AddT;
+  static bool configured = false;      // once per instantiation
+  if (!configured) {
+    cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, true,
+        false, W, a, U, MulT, AddT>,
+        cudaFuncAttributePreferredSharedMemoryCarveout, GB_SPMV_CARVEOUT);
+    cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true,
+        true, W, a, U, MulT, AddT>,
+        cudaFuncAttributePreferredSharedMemoryCarveout, GB_SPMV_CARVEOUT);
+    configured = true;
+  }
+  // 1 = 256-bit loads, 8 consecutive nonzeros per thread (needs 32-byte aligned
+  // arrays); 2 = 32-bit loads, lanes on consecutive nonzeros (any alignment).
+  static const int load_mode = getEnv("GB200_SPMV_LOADS", 1);
+  if ((load_mode == 2 || !aligned) && sizeof(a) == 4)
     spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true, true><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
         extractMul(op), extractAdd(op));

@@ -101,7 +101,7 @@ streamGatherKernel(float* out, const int* colind, const float* val,
 
 typedef graphblas::MinimumPlusSemiring<float> SR;
 
-template <int NT, int IPT, bool Gather>
+template <int NT, int IPT, bool Gather, bool LaneMajor>
 float runMerge(float* w, const int* rowptr, const int* colind, const float* val,
                const float* u, int n, int nnz, int reps, int carveout) {
   SR op;
@@ -112,7 +112,7 @@ float runMerge(float* w, const int* rowptr, const int* colind, const float* val,
   thrust::device_vector<float> cval(nctas);
   spmvMergePartitionKernel<<<(nctas + 256)/256, 256>>>(
       thrust::raw_pointer_cast(tiles.data()), rowptr, n, nnz, nctas, tile);
-  auto kern = spmvMergeKernelT<NT, IPT, true, Gather, false, float, float, float,
+  auto kern = spmvMergeKernelT<NT, IPT, !LaneMajor, Gather, LaneMajor, float, float, float,
       decltype(graphblas::extractMul(op)), decltype(graphblas::extractAdd(op))>;
   if (carveout >= 0)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -209,23 +209,24 @@ int main(int argc, char** argv) {
   }
   report("stream + gather (one chunk per thread)", best);
 
-#define LAB(NT, IPT, G, CARVE)                                               \
+#define LAB(NT, IPT, G, LM, CARVE)                                           \
   { char name[96];                                                           \
-    snprintf(name, sizeof(name), "merge NT=%d IPT=%d gather=%d carveout=%d", \
-             NT, IPT, (int)G, CARVE);                                        \
-    report(name, runMerge<NT, IPT, G>(wp, rp, ci, va, up, (int)n, (int)nnz,  \
-                                      reps, CARVE)); }
-  LAB(128, 15, true, -1)
-  LAB(128, 15, false, -1)
-  LAB(256, 7, true, -1)
-  LAB(256, 7, false, -1)
-  LAB(256, 15, true, -1)
-  LAB(128, 7, true, -1)
-  LAB(128, 23, true, -1)
-  LAB(64, 31, true, -1)
-  LAB(128, 15, true, 25)
-  LAB(128, 15, true, 50)
-  LAB(256, 7, true, 50)
-  LAB(512, 7, true, -1)
+    snprintf(name, sizeof(name),                                             \
+             "merge NT=%d IPT=%d gather=%d lanemajor=%d carveout=%d",        \
+             NT, IPT, (int)G, (int)LM, CARVE);                               \
+    report(name, runMerge<NT, IPT, G, LM>(wp, rp, ci, va, up, (int)n,        \
+                                          (int)nnz, reps, CARVE)); }
+  LAB(128, 7, true, false, 25)
+  LAB(128, 9, true, false, 25)
+  LAB(128, 11, true, false, 25)
+  LAB(128, 15, true, false, 25)
+  LAB(128, 15, true, false, 33)
+  LAB(64, 11, true, false, 25)
+  LAB(64, 15, true, false, 25)
+  LAB(64, 19, true, false, 25)
+  LAB(256, 7, true, false, 25)
+  LAB(256, 9, true, false, 33)
+  LAB(128, 9, true, true, 25)
+  LAB(128, 9, false, false, 25)
   return 0;
 }
