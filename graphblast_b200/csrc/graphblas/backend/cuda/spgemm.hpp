@@ -67,11 +67,22 @@ Info spgemmMasked(SparseMatrix<c>*       C,
         prof_cell = profiler().d_cells + GB_PROF_SPGEMM;
       }
       profiler().begin(GB_PROF_SPGEMM, s);
-      spgemmMaskedKernel<<<grid, GB_SPGEMM_NT, 0, s>>>(C->d_csrVal_,
-          sparse_mask->d_csrRowPtr_, sparse_mask->d_csrColInd_,
-          sparse_mask->d_csrVal_, extractMul(op), extractAdd(op),
-          static_cast<c>(op.identity()), A_csrRowPtr, A_csrColInd, A_csrVal,
-          B_cscColPtr, B_cscRowInd, B_cscVal, A_nrows, work, prof_cell);
+      // GB200_SPGEMM_ROWS=1 selects the warp-per-mask-row form (the reference's
+      // work decomposition) for comparison.
+      static const bool row_form = getEnv("GB200_SPGEMM_ROWS", 0) != 0;
+      if (row_form)
+        spgemmMaskedKernel<<<grid, GB_SPGEMM_NT, 0, s>>>(C->d_csrVal_,
+            sparse_mask->d_csrRowPtr_, sparse_mask->d_csrColInd_,
+            sparse_mask->d_csrVal_, extractMul(op), extractAdd(op),
+            static_cast<c>(op.identity()), A_csrRowPtr, A_csrColInd, A_csrVal,
+            B_cscColPtr, B_cscRowInd, B_cscVal, A_nrows, work, prof_cell);
+      else
+        spgemmMaskedEdgeKernel<<<grid, GB_SPGEMM_NT, 0, s>>>(C->d_csrVal_,
+            sparse_mask->d_csrRowPtr_, sparse_mask->d_csrColInd_,
+            sparse_mask->d_csrVal_, extractMul(op), extractAdd(op),
+            static_cast<c>(op.identity()), A_csrRowPtr, A_csrColInd, A_csrVal,
+            B_cscColPtr, B_cscRowInd, B_cscVal, A_nrows, sparse_mask->nvals_,
+            prof_cell);
       GB_KERNEL_CHECK();
       profiler().end(GB_PROF_SPGEMM, s, 8.0*(A_nrows + 1) +
           8.0*sparse_mask->nvals_);
