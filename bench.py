@@ -41,12 +41,19 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="bfs", choices=["bfs", "sssp", "pr", "tc"])
-    ap.add_argument("--scale", type=int,
-                    default=int(os.environ.get("GB200_BENCH_SCALE", "24")))
+    ap.add_argument("--scale", type=int, default=None,
+                    help="R-MAT scale; default: GB200_BENCH_SCALE, else the scale "
+                         "BASELINE.json names for the algorithm (bfs/sssp 24, "
+                         "pr/tc 22)")
     ap.add_argument("--edgefactor", type=int, default=16)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.scale is None:
+        env = os.environ.get("GB200_BENCH_SCALE")
+        args.scale = int(env) if env else {"bfs": 24, "sssp": 24, "pr": 22,
+                                           "tc": 22}[args.algo]
+    return args
 
 
 class ClockSampler(object):

@@ -16,6 +16,7 @@ namespace backend {
 
 #define GB_SPGEMM_NT 256
 #define GB_SPGEMM_ROWS_PER_GRAB 4
+#define GB_SPGEMM_HEAVY 32        // shorter list longer than this: warp per entry
 
 template <typename c, typename a, typename b, typename m,
           typename MulOp, typename AddOp>
@@ -117,6 +118,8 @@ spgemmMaskedEdgeKernel(c* __restrict__           C_val,
                        const b* __restrict__     B_val,
                        Index                     nrows,
                        Index                     nedges,
+                       Index* __restrict__       heavy_list,   // (entry, row) pairs
+                       unsigned long long*       heavy_count,
                        unsigned long long*       list_bytes) {
   long long scanned = 0;
   Index e = blockIdx.x*blockDim.x + threadIdx.x;
@@ -137,6 +140,15 @@ spgemmMaskedEdgeKernel(c* __restrict__           C_val,
       const Index b_beg = __ldg(B_colptr + j);
       const Index b_end = __ldg(B_colptr + j + 1);
       scanned += (a_end - a_beg) + (b_end - b_beg);
+      const Index shorter = (a_end - a_beg <= b_end - b_beg) ? (a_end - a_beg)
+                                                             : (b_end - b_beg);
+      if (shorter > GB_SPGEMM_HEAVY) {
+        // long x long: a whole warp takes it in the second kernel
+        const unsigned long long slot = atomicAdd(heavy_count, 1ull);
+        heavy_list[2*slot]     = e;
+        heavy_list[2*slot + 1] = row;
+        continue;
+      }
       if (a_end - a_beg <= b_end - b_beg) {
         Index q = b_beg;
         for (Index p = a_beg; p < a_end && q < b_end; ++p) {
@@ -163,6 +175,62 @@ spgemmMaskedEdgeKernel(c* __restrict__           C_val,
     total += __shfl_down_sync(GB_FULL_MASK, total, d);
   if ((threadIdx.x & 31) == 0 && total && list_bytes != NULL)
     atomicAdd(list_bytes, 4ull*total);
+}
+
+// Second kernel of the edge-parallel form: one WARP per deferred mask entry (both
+// lists longer than GB_SPGEMM_HEAVY).  Lanes take every 32nd key of the shorter
+// list and search the longer one, each lane resuming where its last search ended.
+template <typename c, typename a, typename b,
+          typename MulOp, typename AddOp>
+__global__ void __launch_bounds__(GB_SPGEMM_NT)
+spgemmMaskedHeavyKernel(c* __restrict__           C_val,
+                        const Index* __restrict__ mask_colind,
+                        MulOp                     mul_op,
+                        AddOp                     add_op,
+                        c                         identity,
+                        const Index* __restrict__ A_rowptr,
+                        const Index* __restrict__ A_colind,
+                        const a* __restrict__     A_val,
+                        const Index* __restrict__ B_colptr,
+                        const Index* __restrict__ B_rowind,
+                        const b* __restrict__     B_val,
+                        const Index* __restrict__ heavy_list,
+                        const unsigned long long* __restrict__ heavy_count) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long nheavy = *heavy_count;
+  unsigned long long w = (static_cast<unsigned long long>(blockIdx.x)*blockDim.x +
+                          threadIdx.x) >> 5;
+  const unsigned long long nwarps =
+      (static_cast<unsigned long long>(gridDim.x)*blockDim.x) >> 5;
+  for (; w < nheavy; w += nwarps) {
+    const Index e     = heavy_list[2*w];
+    const Index row   = heavy_list[2*w + 1];
+    const Index j     = __ldg(mask_colind + e);
+    const Index a_beg = __ldg(A_rowptr + row);
+    const Index a_end = __ldg(A_rowptr + row + 1);
+    const Index b_beg = __ldg(B_colptr + j);
+    const Index b_end = __ldg(B_colptr + j + 1);
+    c accumulator = identity;
+    if (a_end - a_beg <= b_end - b_beg) {
+      Index q = b_beg;
+      for (Index p = a_beg + lane; p < a_end && q < b_end; p += 32) {
+        const Index key = __ldg(A_colind + p);
+        q = findSorted(B_rowind, q, b_end, key);
+        if (q < b_end && __ldg(B_rowind + q) == key)
+          accumulator = add_op(mul_op(A_val[p], B_val[q]), accumulator);
+      }
+    } else {
+      Index p = a_beg;
+      for (Index q = b_beg + lane; q < b_end && p < a_end; q += 32) {
+        const Index key = __ldg(B_rowind + q);
+        p = findSorted(A_colind, p, a_end, key);
+        if (p < a_end && __ldg(A_colind + p) == key)
+          accumulator = add_op(mul_op(A_val[p], B_val[q]), accumulator);
+      }
+    }
+    accumulator = warpReduce(accumulator, add_op);
+    if (lane == 0) C_val[e] = accumulator;
+  }
 }
 
 }  // namespace backend

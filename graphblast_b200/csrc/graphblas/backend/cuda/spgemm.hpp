@@ -76,13 +76,23 @@ Info spgemmMasked(SparseMatrix<c>*       C,
             sparse_mask->d_csrVal_, extractMul(op), extractAdd(op),
             static_cast<c>(op.identity()), A_csrRowPtr, A_csrColInd, A_csrVal,
             B_cscColPtr, B_cscRowInd, B_cscVal, A_nrows, work, prof_cell);
-      else
+      else {
+        // thread per mask entry; entries whose lists are both long are deferred
+        // to a warp-per-entry kernel through a device-side list (`work` counts it)
+        Index* heavy = reinterpret_cast<Index*>(desc->scratch(GB_SCRATCH_VEC_A,
+            2*static_cast<size_t>(sparse_mask->nvals_ + 1)*sizeof(Index)));
         spgemmMaskedEdgeKernel<<<grid, GB_SPGEMM_NT, 0, s>>>(C->d_csrVal_,
             sparse_mask->d_csrRowPtr_, sparse_mask->d_csrColInd_,
             sparse_mask->d_csrVal_, extractMul(op), extractAdd(op),
             static_cast<c>(op.identity()), A_csrRowPtr, A_csrColInd, A_csrVal,
             B_cscColPtr, B_cscRowInd, B_cscVal, A_nrows, sparse_mask->nvals_,
-            prof_cell);
+            heavy, work, prof_cell);
+        GB_KERNEL_CHECK();
+        spgemmMaskedHeavyKernel<<<grid, GB_SPGEMM_NT, 0, s>>>(C->d_csrVal_,
+            sparse_mask->d_csrColInd_, extractMul(op), extractAdd(op),
+            static_cast<c>(op.identity()), A_csrRowPtr, A_csrColInd, A_csrVal,
+            B_cscColPtr, B_cscRowInd, B_cscVal, heavy, work);
+      }
       GB_KERNEL_CHECK();
       profiler().end(GB_PROF_SPGEMM, s, 8.0*(A_nrows + 1) +
           8.0*sparse_mask->nvals_);
