@@ -37,12 +37,19 @@ Index compactOrdered(Source src, Index nitems, Descriptor* desc) {
   int* block_counts = reinterpret_cast<int*>(
       desc->scratch(GB_SCRATCH_BLOCKSUM, static_cast<size_t>(nblocks)*sizeof(int)));
   // count + (last CTA) scan of the per-CTA counts, then emit: two launches
+  // The total is posted to the host mailbox by the count pass, so the host
+  // learns it while the emit pass is still running.
+  static const bool use_mail = getEnv("GB200_MAILBOX", 1) != 0;
+  const unsigned long long ticket = use_mail ? runtime().mailTicket() : 0ull;
   compactCountScanKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
-      block_counts, nblocks, desc->counters() + 2, ctr);
+      block_counts, nblocks, desc->counters() + 2, ctr,
+      use_mail ? runtime().mailSlot(0) : NULL, ticket);
   GB_KERNEL_CHECK();
   compactEmitKernel<<<nblocks, GB_COMPACT_NT, 0, s>>>(src, nitems,
       block_counts);
   GB_KERNEL_CHECK();
+  if (use_mail)
+    return static_cast<Index>(runtime().mailWait(0, ticket, ctr));
   return static_cast<Index>(runtime().fetch(ctr));
 }
 

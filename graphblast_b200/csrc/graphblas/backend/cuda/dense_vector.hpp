@@ -116,6 +116,7 @@ class DenseVector {
     return GrB_SUCCESS;
   }
   bool vals_stale_;
+  unsigned long long count_ticket_ = 0ull;   // mailbox ticket of the pending count
 
  public:  // (private in the reference; its drivers `#define private public`)
   Index nvals_;  // vector length
@@ -250,7 +251,10 @@ Info DenseVector<T>::computeNnz(Index* nnz_t, T identity, Descriptor* desc) {
     return GrB_SUCCESS;
   }
   if (count_pending_ && nnz_identity_ == identity && d_count_ != NULL) {
-    nnz_ = static_cast<Index>(runtime().fetch(d_count_));
+    // posted to the host mailbox by the producing kernel, or read from the cell
+    nnz_ = (count_ticket_ != 0ull)
+        ? static_cast<Index>(runtime().mailWait(1, count_ticket_, d_count_))
+        : static_cast<Index>(runtime().fetch(d_count_));
     nnz_valid_ = true;
     count_pending_ = false;
     *nnz_t = nnz_;
@@ -541,6 +545,7 @@ Info DenseVector<T>::swap(DenseVector* rhs) {  // NOLINT(build/include_what_you_
   std::swap(bits_valid_,   rhs->bits_valid_);
   std::swap(bits_alloc_words_, rhs->bits_alloc_words_);
   std::swap(vals_stale_,   rhs->vals_stale_);
+  std::swap(count_ticket_, rhs->count_ticket_);
   return GrB_SUCCESS;
 }
 }  // namespace backend

@@ -37,7 +37,8 @@ template <typename Source>
 __global__ void __launch_bounds__(GB_COMPACT_NT)
 compactCountScanKernel(Source src, Index nitems, int* __restrict__ block_counts,
                        int nblocks, unsigned long long* __restrict__ done,
-                       unsigned long long* __restrict__ total_out) {
+                       unsigned long long* __restrict__ total_out,
+                       unsigned long long* mail, unsigned long long ticket) {
   __shared__ int s_scan[GB_COMPACT_NT/32 + 1];
   __shared__ int s_carry;
   __shared__ bool s_last;
@@ -68,6 +69,11 @@ compactCountScanKernel(Source src, Index nitems, int* __restrict__ block_counts,
   if (threadIdx.x == 0) {
     *total_out = static_cast<unsigned long long>(s_carry);
     *done = 0ull;
+    if (mail != NULL) {          // post the total to the host (util.hpp mailbox)
+      *reinterpret_cast<volatile unsigned long long*>(mail) =
+          (ticket << 40) | static_cast<unsigned long long>(s_carry);
+      __threadfence_system();
+    }
   }
 }
 

@@ -420,7 +420,10 @@ spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
                            const Index* __restrict__        rowptr,
                            const Index* __restrict__        colind,
                            unsigned long long*              discovered,
-                           unsigned long long*              inspected_bytes) {
+                           unsigned long long*              inspected_bytes,
+                           unsigned long long*              done,
+                           unsigned long long*              mail,
+                           unsigned long long               ticket) {
   __shared__ int s_red[GB_PULL_NT/32];
   const int lane = threadIdx.x & 31;
   const Index warp0  = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
@@ -457,7 +460,7 @@ spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
       f[j] = static_cast<Index>(-1);
       if (active) {
         f[j] = __ldg(first + row);
-        ++inspected;                      // the 4 bytes of first[row]
+        ++inspected;                      // = colind[rowptr[row]], one entry
       }
     }
     unsigned int pword[GB_PULL_WPI];
@@ -475,7 +478,6 @@ spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
       if (f[j] >= 0 && !(found && UseEarlyExit)) {
         Index k         = __ldg(rowptr + row) + 1;
         const Index end = __ldg(rowptr + row + 1);
-        inspected += 2;
         for (; k < end; ++k) {
           const Index col = __ldg(colind + k);
           ++inspected;
@@ -501,6 +503,19 @@ spmvMaskedOrPullBitsKernel(W* __restrict__                  w,
   int insp = blockSum<GB_PULL_NT>(inspected, s_red);
   if (threadIdx.x == 0 && insp && inspected_bytes != NULL)
     atomicAdd(inspected_bytes, 4ull*static_cast<unsigned long long>(insp));
+  // The CTA that finishes last posts the discovered count to the host mailbox
+  // (util.hpp): the level loop reads it without a stream synchronisation.
+  if (threadIdx.x == 0 && mail != NULL) {
+    __threadfence();
+    if (atomicAdd(done, 1ull) == gridDim.x - 1) {
+      const unsigned long long count =
+          *reinterpret_cast<volatile unsigned long long*>(discovered);
+      *done = 0ull;
+      *reinterpret_cast<volatile unsigned long long*>(mail) =
+          (ticket << 40) | count;
+      __threadfence_system();
+    }
+  }
 }
 
 }  // namespace backend

@@ -157,6 +157,7 @@ Info spmv(DenseVector<W>*        w,
       // a stale shadow costs one 4n-byte pass here.
       const bool bits_form = (op.identity() == static_cast<U>(0));
       bool lazy_vals = false;
+      unsigned long long mail_ticket = 0ull;
       double fixed_bytes;
       if (bits_form) {
         DenseVector<M>* mask_dense =
@@ -187,10 +188,14 @@ Info spmv(DenseVector<W>*        w,
         static const bool eager = getEnv("GB200_EAGER_VALUES", 0) != 0;
         W* w_out = eager ? w->d_val_ : static_cast<W*>(NULL);
         lazy_vals = !eager;
+        static const bool use_mail = getEnv("GB200_MAILBOX", 1) != 0;
+        mail_ticket = use_mail ? runtime().mailTicket() : 0ull;
+        unsigned long long* mail = use_mail ? runtime().mailSlot(1) : NULL;
+        unsigned long long* done = desc->counters() + 4;
 #define GB_LAUNCH_PULL(SC, EE, OR)                                           \
         spmvMaskedOrPullBitsKernel<SC, EE, OR><<<grid, GB_PULL_NT, 0, s>>>(  \
             w_out, w_bits, mask_bits, u_bits, A_nrows, A_first,              \
-            A_csrRowPtr, A_csrColInd, ctr, prof_cell)
+            A_csrRowPtr, A_csrColInd, ctr, prof_cell, done, mail, mail_ticket)
         profiler().begin(GB_PROF_PULL_BOOL, s);
         switch (variant) {
           case 0: GB_LAUNCH_PULL(false, false, false); break;
@@ -204,9 +209,13 @@ Info spmv(DenseVector<W>*        w,
           default: break;
         }
 #undef GB_LAUNCH_PULL
-        // mask bits + output bits [+ output floats] (first-neighbour entries,
-        // rowptr pairs and colind entries are counted where they are read)
-        fixed_bytes = (eager ? 4.0*A_nrows : 0.0) + 0.25*A_nrows;
+        // Algorithmic bytes as SURVEY.md §8d defines them for a Boolean pull
+        // level, at the API's types: 4(n+1) rowptr + 4n visited + 4n written,
+        // plus 4 bytes per colind entry inspected (counted by the kernel; the
+        // first-neighbour summary is colind[rowptr[row]]).  The kernel itself
+        // moves fewer bytes (bitmaps, lazy values) — that is the saving.
+        fixed_bytes = 12.0*A_nrows + 4.0;
+        (void)eager;
       } else {
         CHECK(mask->materialize());
         CHECK(u_t->materialize());
@@ -240,6 +249,7 @@ Info spmv(DenseVector<W>*        w,
       // The kernel wrote 0/1 and counted the ones: the next convert() or
       // a PlusMonoid reduce can reuse the count (one 8-byte read, no pass).
       w->count_pending_ = true;
+      w->count_ticket_  = mail_ticket;     // 0: not posted to the mailbox
       w->zero_one_      = true;
       w->nnz_identity_  = static_cast<W>(0);
       if (desc->debug())

@@ -12,6 +12,7 @@
 #define GRAPHBLAS_BACKEND_CUDA_UTIL_HPP_
 
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -139,7 +140,8 @@ struct Runtime {
   bool         ready;
 
   Runtime() : stream(0), device(0), sm_count(148), h_pinned(NULL),
-              h_pinned_bytes(0), ready(false) {}
+              h_pinned_bytes(0), ready(false), h_mail(NULL), d_mail(NULL),
+              mail_seq(0) {}
 
   void init() {
     if (ready) return;
@@ -173,6 +175,48 @@ struct Runtime {
   }
 
   void sync() { CUDA_CALL(cudaStreamSynchronize(stream)); }
+
+  // ---- mailbox: small results a kernel posts straight into host memory ---------
+  // A per-level count (compaction total, discovered rows) decides what the host
+  // launches next.  Reading it with cudaMemcpyAsync + cudaStreamSynchronize
+  // waits for EVERYTHING queued on the stream and costs ~10 us of idle GPU per
+  // level; instead the kernel that knows the value stores (ticket << 40 | value)
+  // into mapped pinned memory and the host polls that word, so it can go on as
+  // soon as the producing kernel is done, while later kernels still run.
+  unsigned long long* h_mail;     // pinned + mapped, 8 slots
+  unsigned long long* d_mail;
+  unsigned long long  mail_seq;
+
+  void mailInit() {
+    if (h_mail != NULL) return;
+    CUDA_CALL(cudaHostAlloc(reinterpret_cast<void**>(&h_mail),
+        8*sizeof(unsigned long long), cudaHostAllocMapped));
+    for (int i = 0; i < 8; ++i) h_mail[i] = 0ull;
+    CUDA_CALL(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_mail),
+        h_mail, 0));
+    mail_seq = 0;
+  }
+  // Ticket for the next post (24 bits, never 0) and where the kernel writes it.
+  unsigned long long mailTicket() { mailInit(); mail_seq = (mail_seq % 0xfffffeull) + 1; return mail_seq; }
+  unsigned long long* mailSlot(int slot) { mailInit(); return d_mail + slot; }
+  // Value posted under `ticket`; falls back to a stream-ordered read of
+  // d_fallback if the slot was reused by a later post or nothing arrives.
+  unsigned long long mailWait(int slot, unsigned long long ticket,
+                              const unsigned long long* d_fallback) {
+    volatile unsigned long long* p = h_mail + slot;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned long long spin = 0;; ++spin) {
+      const unsigned long long v = *p;
+      const unsigned long long got = v >> 40;
+      if (got == ticket) return v & ((1ull << 40) - 1ull);
+      if (got != 0 && ((got - ticket) & 0xffffffull) < 0x800000ull)
+        break;                                  // overwritten by a later post
+      if ((spin & 0x3ff) == 0x3ff &&
+          std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2))
+        break;
+    }
+    return fetch(d_fallback);
+  }
 };
 
 inline Runtime& runtime() {
