@@ -121,7 +121,9 @@ __global__ void xchgWaitKernel(const char* __restrict__ local, size_t off_counts
                                size_t off_flags, int world,
                                unsigned long long epoch,
                                unsigned long long* d_cells,
-                               long long timeout_cycles, int as_double) {
+                               long long timeout_cycles, int as_double,
+                               unsigned long long* mail,
+                               unsigned long long ticket) {
   const int lane = threadIdx.x;
   bool ok = true;
   if (lane < world) {
@@ -154,7 +156,13 @@ __global__ void xchgWaitKernel(const char* __restrict__ local, size_t off_counts
   }
   for (int d = 16; d > 0; d >>= 1)
     c += __shfl_down_sync(GB_FULL_MASK, c, d);
-  if (lane == 0) d_cells[2] = ok ? c : ~0ull;
+  if (lane == 0) {
+    d_cells[2] = ok ? c : ~0ull;
+    if (mail != NULL && ok && c < (1ull << 40)) {   // host mailbox (util.hpp)
+      *reinterpret_cast<volatile unsigned long long*>(mail) = (ticket << 40) | c;
+      __threadfence_system();
+    }
+  }
 }
 
 // dst[i] |= src[i]
@@ -192,9 +200,14 @@ inline unsigned long long waitRaw(gb200_xchg_s* x, int as_double) {
   cudaStream_t s = gbStream();
   const int par = static_cast<int>(x->epoch & 1ull);
   // ~10 s at 2 GHz: a rank that died must not hang the others' GPUs
+  // integer totals are posted to the host mailbox: no stream synchronisation
+  const bool mail = !as_double;
+  const unsigned long long ticket = mail ? runtime().mailTicket() : 0ull;
   xchgWaitKernel<<<1, 32, 0, s>>>(x->local, x->off_counts[par], x->off_flags,
-      x->world, x->epoch, x->d_cells, 20000000000ll, as_double);
+      x->world, x->epoch, x->d_cells, 20000000000ll, as_double,
+      mail ? runtime().mailSlot(3) : NULL, ticket);
   GB_KERNEL_CHECK();
+  if (mail) return runtime().mailWait(3, ticket, x->d_cells + 2);
   return runtime().fetch(x->d_cells + 2);
 }
 

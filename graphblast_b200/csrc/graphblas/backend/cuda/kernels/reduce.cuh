@@ -47,13 +47,23 @@ reducePartialKernel(T* __restrict__ partials, const U* __restrict__ in,
 template <typename T, typename Op>
 __global__ void __launch_bounds__(GB_REDUCE_NT)
 reduceFinalKernel(T* __restrict__ out, const T* __restrict__ partials,
-                  int nparts, Op op, T identity) {
+                  int nparts, Op op, T identity,
+                  unsigned long long* mail, unsigned long long ticket) {
   __shared__ T s_red[GB_REDUCE_NT/32];
   T acc = identity;
   for (int i = threadIdx.x; i < nparts; i += GB_REDUCE_NT)
     acc = op(acc, partials[i]);
   T total = blockReduce(acc, op, identity, s_red);
-  if (threadIdx.x == 0) *out = total;
+  if (threadIdx.x == 0) {
+    *out = total;
+    if (mail != NULL && sizeof(T) == 4) {   // post to the host (util.hpp mailbox)
+      unsigned int bits;
+      memcpy(&bits, &total, 4);
+      *reinterpret_cast<volatile unsigned long long*>(mail) =
+          (ticket << 40) | static_cast<unsigned long long>(bits);
+      __threadfence_system();
+    }
+  }
 }
 
 // w[row] = fold of A_val[rowptr[row] .. rowptr[row+1]) ; warp per row.
