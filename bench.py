@@ -430,6 +430,35 @@ def main():
                             "cores": 1, "kind": kind, "ms": dt * 1e3,
                             "host_cores_total": os.cpu_count(),
                             "sample": "one full SSSP of the same graph"}
+        elif args.algo == "pr":
+            import oracle_binding as orc
+            kind = "reference" if orc.ref() is not None else "port"
+            fn = orc.ref_pr if kind == "reference" else orc.pr
+            t0 = time.perf_counter()
+            want = fn(h_rp, h_ci, 0.85, 0.0, 10)   # exactly the 10 iterations the GPU ran
+            dt = time.perf_counter() - t0
+            got = result_vec.extractTuples()
+            rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)))
+            # float32 sums of >1e5 terms in two different orders: see DESIGN.md §5
+            parity = bool(rel <= 1e-4)
+            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
+                            "cores": 1, "kind": kind, "ms": dt * 1e3,
+                            "host_cores_total": os.cpu_count(),
+                            "max_rel_err": rel,
+                            "sample": "one full PageRank (10 iterations) of the "
+                                      "same graph"}
+        elif args.algo == "tc" and args.scale <= 20:
+            import oracle_binding as orc
+            kind = "reference" if orc.ref() is not None else "port"
+            fn = orc.ref_tc if kind == "reference" else orc.tc
+            t0 = time.perf_counter()
+            want = int(fn(h_rp, h_ci))
+            dt = time.perf_counter() - t0
+            parity = bool(int(tc_count[0]) == want)
+            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
+                            "cores": 1, "kind": kind, "ms": dt * 1e3,
+                            "host_cores_total": os.cpu_count(),
+                            "sample": "one full triangle count of the same graph"}
 
     out = {
         "metric": "MTEPS", "value": mteps,
