@@ -14,8 +14,8 @@ namespace backend {
 template <typename Source>
 Index compactOrdered(Source src, Index nitems, Descriptor* desc) {
   if (nitems <= 0) return 0;
-  const int nblocks = static_cast<int>(
-      (static_cast<long long>(nitems) + GB_COMPACT_NT - 1) / GB_COMPACT_NT);
+  const long long per_cta = static_cast<long long>(GB_COMPACT_NT)*Source::kGroup;
+  const int nblocks = static_cast<int>((nitems + per_cta - 1) / per_cta);
   unsigned long long* ctr = desc->counters() + 1;
   cudaStream_t s = gbStream();
   // The single-launch look-back form is opt-in: measured on B200 it ties the

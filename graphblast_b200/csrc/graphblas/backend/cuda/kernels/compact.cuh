@@ -42,8 +42,15 @@ compactCountScanKernel(Source src, Index nitems, int* __restrict__ block_counts,
   __shared__ int s_scan[GB_COMPACT_NT/32 + 1];
   __shared__ int s_carry;
   __shared__ bool s_last;
-  Index item = static_cast<Index>(blockIdx.x)*GB_COMPACT_NT + threadIdx.x;
-  int c = (item < nitems) ? src.count(item) : 0;
+  // Source::kGroup consecutive items per thread (bitmap sources: 4 words): a
+  // sparse frontier leaves almost every word empty, and a grid of one tiny item
+  // per thread was launch- and tail-bound.
+  const Index item0 = (static_cast<Index>(blockIdx.x)*GB_COMPACT_NT + threadIdx.x)
+                      *Source::kGroup;
+  int c = 0;
+#pragma unroll
+  for (int g = 0; g < Source::kGroup; ++g)
+    if (item0 + g < nitems) c += src.count(item0 + g);
   int total = blockSum<GB_COMPACT_NT>(c, s_scan);
   if (threadIdx.x == 0) {
     block_counts[blockIdx.x] = total;
@@ -105,12 +112,23 @@ __global__ void __launch_bounds__(GB_COMPACT_NT)
 compactEmitKernel(Source src, Index nitems,
                   const int* __restrict__ block_offsets) {
   __shared__ int s_scan[GB_COMPACT_NT/32 + 1];
-  Index item = static_cast<Index>(blockIdx.x)*GB_COMPACT_NT + threadIdx.x;
-  int c = (item < nitems) ? src.count(item) : 0;
+  const Index item0 = (static_cast<Index>(blockIdx.x)*GB_COMPACT_NT + threadIdx.x)
+                      *Source::kGroup;
+  int cnt[Source::kGroup];
+  int c = 0;
+#pragma unroll
+  for (int g = 0; g < Source::kGroup; ++g) {
+    cnt[g] = (item0 + g < nitems) ? src.count(item0 + g) : 0;
+    c += cnt[g];
+  }
   int total;
   int excl = blockExclusiveScan<GB_COMPACT_NT>(c, s_scan, &total);
-  if (c > 0) src.emit(item, block_offsets[blockIdx.x] + excl);
-  else if (item < nitems) src.finish(item);
+  int pos = block_offsets[blockIdx.x] + excl;
+#pragma unroll
+  for (int g = 0; g < Source::kGroup; ++g) {
+    if (cnt[g] > 0) { src.emit(item0 + g, pos); pos += cnt[g]; }
+    else if (item0 + g < nitems) src.finish(item0 + g);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -217,6 +235,7 @@ compactOnePassKernel(Source src, Index nitems,
 // One item = 8 consecutive elements.  StructOnly: values are not written.
 template <typename T, bool StructOnly>
 struct DenseCompactSource {
+  static const int kGroup = 1;   // an item is already 8 contiguous values
   const T* u;
   T        identity;
   Index    n;
@@ -256,6 +275,7 @@ struct DenseCompactSource {
 //              masked key-value push prunes zeros with updateFlag/streamCompact).
 template <typename T, bool KeyValue, bool DropZero>
 struct BitmapCompactSource {
+  static const int kGroup = 4;   // 4 bitmap words per thread
   unsigned int* bits;
   T*            acc;
   T             identity;
@@ -313,6 +333,7 @@ struct BitmapCompactSource {
 // identity 0.  Read-only: one item = one word.
 template <typename T, bool StructOnly>
 struct DenseBitsCompactSource {
+  static const int kGroup = 4;
   const unsigned int* bits;
   const T*            u;
   Index*              out_ind;
@@ -339,6 +360,7 @@ struct DenseBitsCompactSource {
 // streamCompact prune "== val").  One item = one entry.
 template <typename T, typename M, bool UseScmp>
 struct SparseAssignFilterSource {
+  static const int kGroup = 1;
   const Index* in_ind;
   const T*     in_val;
   const M*     mask;     // dense mask values
