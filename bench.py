@@ -452,7 +452,7 @@ def main():
             kind = "reference" if orc.ref() is not None else "port"
             fn = orc.ref_tc if kind == "reference" else orc.tc
             t0 = time.perf_counter()
-            want = int(fn(h_rp, h_ci))
+            want = int(fn(lr, lc))          # the reference driver counts on tril(A)
             dt = time.perf_counter() - t0
             parity = bool(int(tc_count[0]) == want)
             cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
