@@ -1,5 +1,7 @@
 // graphblast_b200 backend — host driver for the ordered compaction kernels
-// (kernels/compact.cuh).  Three launches and ONE 8-byte device-to-host read.
+// (kernels/compact.cuh).  Two launches (count pass whose last CTA scans the per-CTA
+// counts, emit pass); the total reaches the host through the mailbox
+// (util.hpp) while the emit pass is still running.
 #ifndef GRAPHBLAS_BACKEND_CUDA_COMPACT_HPP_
 #define GRAPHBLAS_BACKEND_CUDA_COMPACT_HPP_
 

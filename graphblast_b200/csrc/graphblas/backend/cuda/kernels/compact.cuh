@@ -1,5 +1,5 @@
-// graphblast_b200 backend — ORDERED stream compaction in three small kernels
-// (count per CTA -> scan of CTA counts -> emit).  Output order equals input
+// graphblast_b200 backend — ORDERED stream compaction in two small kernels
+// (count per CTA, whose last CTA scans the CTA counts -> emit).  Output order equals input
 // order, so a compacted bitmap yields a sorted, duplicate-free index list with
 // no sort at all — this is what replaces the reference's
 // radix-sort + reduce-by-key in the push direction
@@ -19,16 +19,6 @@ namespace graphblas {
 namespace backend {
 
 #define GB_COMPACT_NT 256
-
-template <typename Source>
-__global__ void __launch_bounds__(GB_COMPACT_NT)
-compactCountKernel(Source src, Index nitems, int* __restrict__ block_counts) {
-  __shared__ int s_red[GB_COMPACT_NT/32];
-  Index item = static_cast<Index>(blockIdx.x)*GB_COMPACT_NT + threadIdx.x;
-  int c = (item < nitems) ? src.count(item) : 0;
-  int total = blockSum<GB_COMPACT_NT>(c, s_red);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
-}
 
 // Count pass with the scan folded in: the CTA that finishes last (a counter that
 // it leaves at zero again) scans the per-CTA counts in place, so the ordered
@@ -82,29 +72,6 @@ compactCountScanKernel(Source src, Index nitems, int* __restrict__ block_counts,
       __threadfence_system();
     }
   }
-}
-
-// Single CTA: in-place exclusive scan of block_counts[0..nblocks), total to
-// *total_out (64-bit cell).
-__global__ void __launch_bounds__(1024)
-compactScanKernel(int* __restrict__ block_counts, int nblocks,
-                  unsigned long long* __restrict__ total_out) {
-  __shared__ int s_scan[1024/32 + 1];
-  __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nblocks; base += 1024) {
-    int i = base + threadIdx.x;
-    int v = (i < nblocks) ? block_counts[i] : 0;
-    int total;
-    int excl = blockExclusiveScan<1024>(v, s_scan, &total);
-    int carry = s_carry;
-    if (i < nblocks) block_counts[i] = carry + excl;
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry = carry + total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total_out = static_cast<unsigned long long>(s_carry);
 }
 
 template <typename Source>

@@ -9,10 +9,13 @@
 //                           Replaces mgpu::SpmvCsrBinary (reference spmv.hpp:188-190,
 //                           ext/moderngpu/include/kernels/spmvcsr.cuh:334-413,489-587:
 //                           5+ launches and 2 device syncs per SpMV).
-//  * spmvMaskedOrPullKernel: fused mask + OR-AND + early-exit + operand-reuse
-//                           Boolean pull (reference kernels/spmv.hpp:7-59), plus a
-//                           fused count of discovered rows so the direction switch
-//                           needs no extra pass.
+//  * spmvMaskedOrPullKernel / spmvMaskedOrPullBitsKernel: fused mask + OR-AND +
+//                           early-exit + operand-reuse Boolean pull (reference
+//                           kernels/spmv.hpp:7-59).  The Bits form (identity 0) reads
+//                           mask and frontier as bitmaps, decides most rows from a
+//                           per-matrix first-neighbour summary, publishes the result
+//                           as a bitmap + count (values are materialised lazily) and
+//                           posts the count to the host mailbox.
 //
 // Algorithmic bytes per launch:
 //   merge SpMV : 4(n+1) rowptr + 8 nnz colind/val + 4n gather (once) + 4n write
