@@ -155,6 +155,16 @@ frontierDegreeScanKernel(Index* __restrict__ offs,
   }
 }
 
+// Posts one device-side Index to the host mailbox (backend/cuda/util.hpp).
+__global__ void postIndexKernel(const Index* __restrict__ value,
+                                unsigned long long* mail,
+                                unsigned long long ticket) {
+  *reinterpret_cast<volatile unsigned long long*>(mail) =
+      (ticket << 40) | static_cast<unsigned long long>(
+          static_cast<unsigned int>(*value));
+  __threadfence_system();
+}
+
 // Binary search helper kept for API parity with reference kernels/util.hpp:8-24.
 __device__ __forceinline__ Index binarySearch(const Index* array, Index target,
                                               Index begin, Index end) {

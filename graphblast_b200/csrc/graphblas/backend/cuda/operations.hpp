@@ -111,11 +111,21 @@ Info mxvDispatch(Vector<W>*       w,
   }
   CHECK(u->getStorage(&u_vec_type));
 
-  if (A_mat_type == GrB_SPARSE && u_vec_type == GrB_SPARSE) {
+  bool run_pull = !(A_mat_type == GrB_SPARSE && u_vec_type == GrB_SPARSE);
+  if (!run_pull) {
     if (lb_mode == GrB_LOAD_BALANCE_MERGE) {
       CHECK(w->setStorage(GrB_SPARSE));
+      // In the automatic mode the push may hand the call back when the frontier
+      // owns too many of the edges (spmspv.hpp); both orientations must exist.
+      bool prefer_pull = false;
+      const bool may_switch = (mxv_mode == GrB_PUSHPULL) &&
+          (A_symmetric || A_format == GrB_SPARSE_MATRIX_CSRCSC);
       CHECK(spmspvMerge(&w->sparse_, mask, accum, op, &A->sparse_,
-          &u->sparse_, desc));
+          &u->sparse_, desc, may_switch ? &prefer_pull : NULL));
+      if (prefer_pull) {
+        CHECK(u_t->sparse2dense(op.identity(), desc));
+        run_pull = true;
+      }
     } else if (lb_mode == GrB_LOAD_BALANCE_SIMPLE) {
       std::cout << "Simple SPMSPV not implemented yet!\n";
       return GrB_NOT_IMPLEMENTED;
@@ -125,8 +135,9 @@ Info mxvDispatch(Vector<W>*       w,
     } else {
       std::cout << "Error: Invalid load-balance algorithm!\n";
     }
-    desc->lastmxv_ = GrB_PUSHONLY;
-  } else {
+    if (!run_pull) desc->lastmxv_ = GrB_PUSHONLY;
+  }
+  if (run_pull) {
     if (IsVxm) CHECK(w->setStorage(GrB_DENSE));
     else       CHECK(w->sparse2dense(op.identity(), desc));
     if (A_mat_type == GrB_SPARSE) {

@@ -80,7 +80,16 @@ Info spmspvMerge(SparseVector<W>*       w,
                  SemiringT              op,
                  const SparseMatrix<a>* A,
                  const SparseVector<U>* u,
-                 Descriptor*            desc) {
+                 Descriptor*            desc,
+                 bool*                  prefer_pull = NULL) {
+  // prefer_pull != NULL: the caller can still take the pull direction.  If the
+  // frontier's edges are more than GB200_EDGE_SWITCH_PCT percent of all stored entries the
+  // push is abandoned before it starts (*prefer_pull = true, w untouched): the
+  // reference switches on the frontier's VERTEX share only (vector.hpp:318-342),
+  // and a few hub vertices below that threshold can own most of the graph — at
+  // RMAT-24 one such SSSP push expanded 2.9 GB of edges in 4.2 ms where the pull
+  // over everything takes 2.1 ms.
+  if (prefer_pull != NULL) *prefer_pull = false;
   // Get descriptor parameters for SCMP, REPL, TRAN
   Desc_value scmp_mode, repl_mode, inp0_mode, inp1_mode;
   CHECK(desc->get(GrB_MASK, &scmp_mode));
@@ -155,6 +164,34 @@ Info spmspvMerge(SparseVector<W>*       w,
     void* cub_tmp = desc->scratch(GB_SCRATCH_CUB, cub_bytes);
     CUDA_CALL(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, deg, offs,
         nf + 1, s));
+  }
+
+  // 1b) edge-based direction check (only for frontiers big enough to matter, so
+  //     the small levels of a BFS pay nothing for it)
+  static const float edge_switch =
+      0.01f*static_cast<float>(getEnv("GB200_EDGE_SWITCH_PCT", 33));
+  if (prefer_pull != NULL && edge_switch > 0.f && nf >= 4096) {
+    const unsigned long long ticket = runtime().mailTicket();
+    postIndexKernel<<<1, 1, 0, s>>>(offs + nf, runtime().mailSlot(4), ticket);
+    GB_KERNEL_CHECK();
+    long long ef = -1;
+    volatile unsigned long long* slot = runtime().h_mail + 4;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned long long spin = 0;; ++spin) {
+      const unsigned long long v = *slot;
+      if ((v >> 40) == ticket) { ef = static_cast<long long>(v & 0xffffffffull); break; }
+      if ((spin & 0x3ff) == 0x3ff &&
+          std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2))
+        break;
+    }
+    if (ef < 0) ef = runtime().fetch(offs + nf);
+    if (static_cast<double>(ef) > static_cast<double>(edge_switch)*A->nvals_) {
+      if (desc->dirinfo())
+        std::cout << "Frontier owns " << ef << " of " << A->nvals_
+                  << " entries: pull instead of push\n";
+      *prefer_pull = true;
+      return GrB_SUCCESS;
+    }
   }
 
   // 2) expand + combine into the accumulator / bitmap.
