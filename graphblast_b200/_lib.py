@@ -99,6 +99,7 @@ SIGNATURES = [
     ("gb200_dist_bfs", _I, [_P, _P, _P, _LL, _LL, _P, C.POINTER(_I)]),
     ("gb200_xchg_allgather_words", _I, [_P, _P, _D, C.POINTER(_D)]),
     ("gb200_dist_pr", _I, [_P, _P, _P, _LL, _F, _F, _P, C.POINTER(_I)]),
+    ("gb200_dist_sssp", _I, [_P, _P, _P, _LL, _LL, _P, C.POINTER(_I)]),
 ]
 
 

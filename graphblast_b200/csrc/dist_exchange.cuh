@@ -38,6 +38,8 @@ struct gb200_xchg_s {
   graphblas::Vector<float>* f_glob;
   // vectors of the PageRank loop: p_glob, p_prev_own, p_swap, r, r_temp
   graphblas::Vector<float>* pr_vec[5];
+  // vectors of the SSSP loop: frontier_glob (view), relaxed, improved
+  graphblas::Vector<float>* ss_vec[3];
 };
 
 namespace gbx {
@@ -261,6 +263,7 @@ int gb200_xchg_create(gb200_xchg_t* out, int world, int rank,
         cudaMemcpyHostToDevice));
   x->f_own = NULL; x->f2 = NULL; x->f_glob = NULL;
   for (int i = 0; i < 5; ++i) x->pr_vec[i] = NULL;
+  for (int i = 0; i < 3; ++i) x->ss_vec[i] = NULL;
   *out = x;
   return 0;
 }
@@ -306,6 +309,7 @@ int gb200_xchg_free(gb200_xchg_t x) {
   cudaFree(x->d_seed); cudaFree(x->d_peer);
   delete x->f_own; delete x->f2; delete x->f_glob;
   for (int i = 0; i < 5; ++i) delete x->pr_vec[i];
+  for (int i = 0; i < 3; ++i) delete x->ss_vec[i];
   delete x;
   return 0;
 }
@@ -521,6 +525,103 @@ int gb200_dist_pr(gb200_xchg_t x, gb200_vector_t p, gb200_matrix_t M,
   }
   d->set(GrB_MXVMODE, saved_mode);
   if (iters_out != NULL) *iters_out = iter - 1;
+  return rc(info);
+}
+
+// SSSP over the 1-D row partition: the loop of reference
+// graphblas/algorithm/sssp.hpp:46-99 on the owned slice.  The exchange carries one
+// word per VERTEX (the frontier's float values, FLT_MAX = absent) and the number of
+// improved vertices as the partial.  v (length nl) = owned distances (output);
+// M = owned rows of A^T (weights A(i,j) at M(j,i)), (nl x n), CSR + CSC.  The
+// direction of every round is chosen by mxv itself (GrB_PUSHPULL: frontier ratio,
+// hysteresis and the edge-share check), exactly as on one GPU.
+int gb200_dist_sssp(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
+                    long long n, long long source, gb200_desc_t desc,
+                    int* rounds_out) {
+  if (x == NULL || v == NULL || M == NULL || desc == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  if (!x->connected || M->f == NULL) return rc(graphblas::GrB_UNINITIALIZED_OBJECT);
+  GB200_REQUIRE_DEVICE();
+  using namespace graphblas;          // NOLINT(build/namespaces)
+  Descriptor* d = &desc->desc;
+  const float kInf = std::numeric_limits<float>::max();
+  const size_t lo = x->word_off[x->rank];
+  Index nl;
+  CHECK(v->f->size(&nl));
+  if (static_cast<size_t>(nl) != x->word_off[x->rank + 1] - lo ||
+      x->total_words != static_cast<size_t>(n))
+    return rc(GrB_DIMENSION_MISMATCH);
+  if (x->ss_vec[0] == NULL) {
+    x->ss_vec[0] = new Vector<float>(static_cast<Index>(n));   // frontier (view)
+    x->ss_vec[1] = new Vector<float>(nl);                      // relaxed
+    x->ss_vec[2] = new Vector<float>(nl);                      // improved
+  }
+  Vector<float>* frontier = x->ss_vec[0];
+  Vector<float>* relaxed  = x->ss_vec[1];
+  Vector<float>* improved = x->ss_vec[2];
+  gb200_vector_s relaxed_h = {GB200_FP32, relaxed};
+
+  const bool own_src = source >= static_cast<long long>(lo) &&
+                       source < static_cast<long long>(lo) + nl;
+  CHECK(v->f->fill(kInf));
+  CHECK(relaxed->fill(kInf));
+  if (own_src) {
+    CHECK(v->f->setElement(0.f, static_cast<Index>(source - lo)));
+    CHECK(relaxed->setElement(0.f, static_cast<Index>(source - lo)));
+  }
+  void* r_dev = NULL;
+  if (gb200_vector_device_ptr(&relaxed_h, &r_dev) != 0) return rc(GrB_PANIC);
+  double total = 0.0;
+  int info_i = gb200_xchg_allgather_words(x, r_dev, own_src ? 1.0 : 0.0, &total);
+  if (info_i != 0) return info_i;
+
+  const int max_niter = d->descriptor_.max_niter_;
+  const float switchpoint = d->descriptor_.switchpoint();
+  bool  sparse_mode = true;     // the source frontier is built sparse
+  float prev_ratio  = 0.f;
+  Info info = GrB_SUCCESS;
+  int round;
+  for (round = 1; round <= max_niter && total > 0.0; ++round) {
+    float* data = const_cast<float*>(
+        reinterpret_cast<const float*>(gbx::current(x)));
+    info = frontier->build(data, static_cast<Index>(n));          if (info) break;
+    // The gathered frontier arrives dense every round; on one GPU it would still
+    // be SPARSE while it is small (it is the sparse output of the previous push),
+    // and mxv's own conversion rule only turns a dense vector sparse when it
+    // shrinks.  Carry the storage state of reference vector.hpp:318-342 across
+    // rounds here and hand mxv the storage the single-GPU loop would have had.
+    const float ratio = static_cast<float>(total/static_cast<double>(n));
+    if (sparse_mode) {
+      if (ratio > switchpoint && ratio > prev_ratio) sparse_mode = false;
+      else prev_ratio = ratio;
+    } else {
+      if (ratio <= switchpoint && ratio < prev_ratio) sparse_mode = true;
+      else prev_ratio = ratio;
+    }
+    if (sparse_mode) {
+      info = frontier->vector_.dense2sparse(kInf, &d->descriptor_); if (info) break;
+    }
+    info = mxv<float, float, float, float>(relaxed, GrB_NULL, GrB_NULL,
+        MinimumPlusSemiring<float>(), M->f, frontier, d);         if (info) break;
+    info = eWiseAdd<float, float, float, float>(improved, GrB_NULL, GrB_NULL,
+        CustomLessPlusSemiring<float>(), relaxed, v->f, d);       if (info) break;
+    info = eWiseAdd<float, float, float, float>(v->f, GrB_NULL, GrB_NULL,
+        MinimumPlusSemiring<float>(), v->f, relaxed, d);          if (info) break;
+    CHECK(d->toggle(GrB_MASK));
+    info = assign<float, float, float, Index>(relaxed, improved, GrB_NULL, kInf,
+        GrB_ALL, nl, d);
+    CHECK(d->toggle(GrB_MASK));
+    if (info) break;
+    float succ = 0.f;
+    info = reduce<float, float>(&succ, GrB_NULL, PlusMonoid<float>(), improved,
+        d);                                                       if (info) break;
+    // the owned part of the next frontier, as a dense float slice
+    info = relaxed->vector_.sparse2dense(kInf, &d->descriptor_);  if (info) break;
+    if (gb200_vector_device_ptr(&relaxed_h, &r_dev) != 0) { info = GrB_PANIC; break; }
+    if (gb200_xchg_allgather_words(x, r_dev, static_cast<double>(succ),
+                                   &total) != 0) { info = GrB_PANIC; break; }
+  }
+  if (rounds_out != NULL) *rounds_out = round - 1;
   return rc(info);
 }
 

@@ -276,6 +276,15 @@ int gb200_dist_pr(gb200_xchg_t x, gb200_vector_t p, gb200_matrix_t M,
                   long long n, float alpha, float eps, gb200_desc_t desc,
                   int* iters_out);
 
+/* SSSP over the 1-D row partition: the loop of reference
+ * graphblas/algorithm/sssp.hpp:46-99 on the owned slice; frontier values (floats,
+ * one word per vertex) and the number of improved vertices exchanged per round.
+ * v = owned distances (FLT_MAX = unreachable); M = owned rows of A^T (owned x n,
+ * CSR + CSC, weights).  Runs until no vertex improves or desc max_niter rounds. */
+int gb200_dist_sssp(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
+                    long long n, long long source, gb200_desc_t desc,
+                    int* rounds_out);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

@@ -137,3 +137,52 @@ def test_two_ranks_pagerank():
     res = json.loads(lines[0])
     assert res["n_gpus"] == 2
     assert res["parity_vs_cpu_reference"] is True, res["max_rel_err"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [10, 15])
+def test_native_sssp_world1(scale):
+    """gb200_dist_sssp on one rank against the oracle: bit-exact distances."""
+    import graphblast_b200 as gb
+    from graphblast_b200 import dist as gdist, graphs
+    dev = torch.device("cuda", 0)
+    rp, ci = orc.rmat_csr(scale)
+    n = len(rp) - 1
+    nnz = len(ci)
+    w = gb.api.host_uniform_weights(1, 1, 64, nnz)
+    rowptr = torch.from_numpy(rp).to(dev)
+    colind = torch.from_numpy(ci).to(dev)
+    d_wt = graphs.transpose_values(n, rowptr, colind, torch.from_numpy(w).to(dev))
+    M, keep = gdist.weighted_local_matrix(gb, n, rowptr, colind, d_wt, 0, n)
+    v = gb.Vector(n)
+    desc = gb.Descriptor(mxvmode=0, switchpoint=0.025)
+    comm = gdist.Comm([0, n], dev)
+    x = gdist.PeerExchange(gb, comm, dev, offsets=[0, n])
+    try:
+        deg = np.diff(rp)
+        for source in (int(np.argmax(deg)), int(np.nonzero(deg)[0][-1])):
+            want = orc.sssp(rp, ci, w, source)
+            for _ in range(2):
+                rounds = x.sssp(v, M, n, source, desc)
+                assert rounds >= 1
+                assert np.array_equal(v.extractTuples()[:n], want)
+    finally:
+        x.close()
+
+
+@pytest.mark.gpu
+def test_two_ranks_sssp():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, GB200_BENCH_SCALE="18")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "bench.py"),
+           "--gpus", "2", "--algo", "sssp", "--steps", "2", "--warmup", "1"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    res = json.loads(lines[0])
+    assert res["n_gpus"] == 2
+    assert res["parity_vs_cpu_reference"] is True
