@@ -612,13 +612,22 @@ int gb200_dist_sssp(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
         GrB_ALL, nl, d);
     CHECK(d->toggle(GrB_MASK));
     if (info) break;
-    float succ = 0.f;
-    info = reduce<float, float>(&succ, GrB_NULL, PlusMonoid<float>(), improved,
-        d);                                                       if (info) break;
-    // the owned part of the next frontier, as a dense float slice
-    info = relaxed->vector_.sparse2dense(kInf, &d->descriptor_);  if (info) break;
+    // Owned part of the next frontier: its entry count is this rank's partial (the
+    // single-GPU loop stops on "frontier empty or nothing improved"; nothing
+    // improved means every entry was just masked back to FLT_MAX, so the count
+    // covers both), its values go out as a dense float slice.
+    Index cnt = 0;
+    Storage r_type;
+    CHECK(relaxed->vector_.getStorage(&r_type));
+    if (r_type == GrB_SPARSE) {
+      CHECK(relaxed->vector_.sparse_.nvals(&cnt));
+      info = relaxed->vector_.sparse2dense(kInf, &d->descriptor_); if (info) break;
+    } else {
+      info = relaxed->vector_.dense_.computeNnz(&cnt, kInf, &d->descriptor_);
+      if (info) break;
+    }
     if (gb200_vector_device_ptr(&relaxed_h, &r_dev) != 0) { info = GrB_PANIC; break; }
-    if (gb200_xchg_allgather_words(x, r_dev, static_cast<double>(succ),
+    if (gb200_xchg_allgather_words(x, r_dev, static_cast<double>(cnt),
                                    &total) != 0) { info = GrB_PANIC; break; }
   }
   if (rounds_out != NULL) *rounds_out = round - 1;

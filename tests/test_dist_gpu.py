@@ -164,7 +164,7 @@ def test_native_sssp_world1(scale):
             want = orc.sssp(rp, ci, w, source)
             for _ in range(2):
                 rounds = x.sssp(v, M, n, source, desc)
-                assert rounds >= 1
+                assert 1 <= rounds < 200          # stops when the frontier is empty
                 assert np.array_equal(v.extractTuples()[:n], want)
     finally:
         x.close()
