@@ -127,3 +127,32 @@ def test_exchange_record_roundtrip_single_rank():
     g, total = comm.exchange()
     assert g[:3].tolist() == [5, -2 ** 31, 7]
     assert total == 2 ** 33 + 5
+
+
+def test_local_slice_permutation_carries_values():
+    """local_slice(return_order=True): val[order] are the CSC values of the owned
+    rows, i.e. the (colptr, rowind, val[order]) triple is the transpose of
+    (rp_local, ci_local, val) — what weighted_local_matrix hands to the library."""
+    rp, ci = orc.rmat_csr(9)
+    n = len(rp) - 1
+    rowptr = torch.from_numpy(rp)
+    colind = torch.from_numpy(ci)
+    rng = np.random.RandomState(3)
+    val = torch.from_numpy(rng.randint(1, 65, size=len(ci)).astype(np.float32))
+    for lo, hi in ((0, n), (64, 320), (n - 128, n)):
+        rp_l, ci_l, colptr, rowind, order = gdist.local_slice(
+            rowptr, colind, lo, hi, n, return_order=True)
+        e0, e1 = int(rp[lo]), int(rp[hi])
+        val_l = val[e0:e1]
+        cval = val_l[order]
+        dense = np.zeros((hi - lo, n), dtype=np.float32)
+        rp_n, ci_n = rp_l.numpy(), ci_l.numpy()
+        for r in range(hi - lo):
+            dense[r, ci_n[rp_n[r]:rp_n[r + 1]]] = val_l.numpy()[rp_n[r]:rp_n[r + 1]]
+        cp, ri, cv = colptr.numpy(), rowind.numpy(), cval.numpy()
+        assert cp[-1] == e1 - e0
+        for c in range(n):
+            rows = ri[cp[c]:cp[c + 1]]
+            assert np.all(np.diff(rows) > 0)                 # sorted, unique
+            assert np.array_equal(dense[rows, c], cv[cp[c]:cp[c + 1]])
+        assert np.count_nonzero(dense) == e1 - e0
