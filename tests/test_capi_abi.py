@@ -99,3 +99,22 @@ def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.ExtensionMissing):
         _lib.load()
+
+
+def test_header_is_plain_c():
+    """include/graphblast_b200.h must compile as C99 (it is what cgo / JNI / Rust
+    FFI bindings of this path would include)."""
+    import subprocess
+    import tempfile
+    src = '#include "graphblast_b200.h"\nint main(void) { return 0; }\n'
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write(src)
+        path = f.name
+    try:
+        out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic",
+                              "-Werror", "-I", os.path.join(ROOT, "include"),
+                              "-fsyntax-only", path],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    finally:
+        os.unlink(path)
