@@ -118,3 +118,25 @@ def test_header_is_plain_c():
         assert out.returncode == 0, out.stderr
     finally:
         os.unlink(path)
+
+
+def test_c_example_links_and_fails_loudly_without_a_device():
+    """examples/capi_bfs.c builds with gcc alone against the shared library; on a
+    box without a GPU it must refuse to run (no CPU fallback), not compute."""
+    import subprocess
+    import torch
+    out = os.path.join(ROOT, "build", "capi_bfs_test")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    lib_dir = os.path.join(ROOT, "graphblast_b200", "lib")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I",
+                         os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "examples", "capi_bfs.c"), "-L", lib_dir,
+                         "-lgraphblast_b200", "-Wl,-rpath," + lib_dir, "-o", out],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    if torch.cuda.is_available():
+        return                       # the GPU run is tests/test_dropin_gpu.py's job
+    run = subprocess.run([out, os.path.join(ROOT, "tests", "golden", "chesapeake.mtx")],
+                         capture_output=True, text=True)
+    assert run.returncode != 0
+    assert "no CUDA device" in run.stderr
