@@ -135,7 +135,7 @@ def test_c_example_links_and_fails_loudly_without_a_device():
                         capture_output=True, text=True)
     assert cc.returncode == 0, cc.stderr
     if torch.cuda.is_available():
-        return                       # the GPU run is tests/test_dropin_gpu.py's job
+        return                       # the GPU run is tests/test_zz_c_example_gpu.py's job
     run = subprocess.run([out, os.path.join(ROOT, "tests", "golden", "chesapeake.mtx")],
                          capture_output=True, text=True)
     assert run.returncode != 0
