@@ -195,6 +195,13 @@ def run_reference_arm(args):
         w = gb.api.host_uniform_weights(args.seed, 1, 64, nnz)
         step = (lambda: orc.ref_sssp(h_rp, h_ci, w, source)) if kind == "reference" \
             else (lambda: orc.sssp(h_rp, h_ci, w, source))
+    elif args.algo == "pr":
+        step = (lambda: orc.ref_pr(h_rp, h_ci, 0.85, 0.0, 10)) if kind == "reference" \
+            else (lambda: orc.pr(h_rp, h_ci, 0.85, 0.0, 10))
+    elif args.algo == "tc":
+        lr, lc = orc.tril(h_rp, h_ci)        # the reference driver counts on tril(A)
+        step = (lambda: orc.ref_tc(lr, lc)) if kind == "reference" \
+            else (lambda: orc.tc(lr, lc))
     else:
         step = (lambda: orc.ref_bfs(h_rp, h_ci, source)) if kind == "reference" \
             else (lambda: orc.bfs(h_rp, h_ci, source))
@@ -215,7 +222,8 @@ def run_reference_arm(args):
         "config": workload_config(args, n, nnz, source),
         "cpu_baseline": {"value": mteps, "unit": "MTEPS", "cores": 1,
                          "kind": kind,
-                         "sample": "one full traversal of the same graph per step"},
+                         "sample": "one full run of the same algorithm on the same "
+                                   "graph per step (sequential code: 1 host thread)"},
         "e2e": {"value": mteps, "unit": "MTEPS", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
