@@ -292,8 +292,71 @@ Info spmv(DenseVector<W>*        w,
       A_t->spmv_tiles_nvals_[which] = A->nvals_;
       A_t->spmv_tiles_count_[which] = ntiles;
     }
+    // Experimental, off by default (GB200_SPMV_RELABEL=1, read per call): gather
+    // from a copy of u permuted by descending column reference count through a
+    // relabelled copy of the column indices.  The products and their order are
+    // unchanged (results are bit-identical); only the gather addresses move, so
+    // that the hub columns sit in one contiguous, L1/L2-resident prefix.  Costs
+    // 4 bytes per stored entry of device memory and one n-element permutation
+    // pass per call.  Not measured in r01 (written after the GPU budget was spent).
+    const Index* gather_ci = A_csrColInd;
+    const U*     gather_u  = u_t->d_val_;
+    {
+      const char* env = std::getenv("GB200_SPMV_RELABEL");
+      if (env != NULL && atoi(env) != 0 && A->nvals_ > 0 && sizeof(Index) == 4) {
+        const Index ncols_t = use_tran ? A->nrows_ : A->ncols_;
+        if (A_t->d_relabel_ci_[which] == NULL ||
+            A_t->relabel_key_[which] != A_csrColInd ||
+            A_t->relabel_nvals_[which] != A->nvals_) {
+          if (A_t->d_relabel_ci_[which] != NULL) gbFree(A_t->d_relabel_ci_[which]);
+          if (A_t->d_relabel_perm_[which] != NULL) gbFree(A_t->d_relabel_perm_[which]);
+          A_t->d_relabel_ci_[which] = reinterpret_cast<Index*>(
+              gbMalloc(static_cast<size_t>(A->nvals_)*sizeof(Index)));
+          A_t->d_relabel_perm_[which] = reinterpret_cast<Index*>(
+              gbMalloc(static_cast<size_t>(ncols_t)*sizeof(Index)));
+          // scratch: counts, sorted counts, identity ids, rank
+          int*   cnt   = reinterpret_cast<int*>(gbMalloc(
+              static_cast<size_t>(ncols_t)*sizeof(int)));
+          int*   cnt_s = reinterpret_cast<int*>(gbMalloc(
+              static_cast<size_t>(ncols_t)*sizeof(int)));
+          Index* ids   = reinterpret_cast<Index*>(gbMalloc(
+              static_cast<size_t>(ncols_t)*sizeof(Index)));
+          Index* rank  = reinterpret_cast<Index*>(gbMalloc(
+              static_cast<size_t>(ncols_t)*sizeof(Index)));
+          CUDA_CALL(cudaMemsetAsync(cnt, 0,
+              static_cast<size_t>(ncols_t)*sizeof(int), s));
+          columnCountKernel<<<gridFor(A->nvals_, 256, 8), 256, 0, s>>>(cnt,
+              A_csrColInd, A->nvals_);
+          GB_KERNEL_CHECK();
+          iotaKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(ids, ncols_t);
+          GB_KERNEL_CHECK();
+          size_t tmp_bytes = 0;
+          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(NULL, tmp_bytes, cnt,
+              cnt_s, ids, A_t->d_relabel_perm_[which], ncols_t, 0, 32, s));
+          void* tmp = gbMalloc(tmp_bytes);
+          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, cnt,
+              cnt_s, ids, A_t->d_relabel_perm_[which], ncols_t, 0, 32, s));
+          invertPermKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(rank,
+              A_t->d_relabel_perm_[which], ncols_t);
+          GB_KERNEL_CHECK();
+          relabelKernel<<<gridFor(A->nvals_, 256, 8), 256, 0, s>>>(
+              A_t->d_relabel_ci_[which], A_csrColInd, rank, A->nvals_);
+          GB_KERNEL_CHECK();
+          gbFree(tmp); gbFree(rank); gbFree(ids); gbFree(cnt_s); gbFree(cnt);
+          A_t->relabel_key_[which]   = A_csrColInd;
+          A_t->relabel_nvals_[which] = A->nvals_;
+        }
+        U* u_perm = reinterpret_cast<U*>(desc->scratch(GB_SCRATCH_VEC_B,
+            static_cast<size_t>(ncols_t)*sizeof(U)));
+        permuteGatherKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(u_perm,
+            u_t->d_val_, A_t->d_relabel_perm_[which], ncols_t);
+        GB_KERNEL_CHECK();
+        gather_ci = A_t->d_relabel_ci_[which];
+        gather_u  = u_perm;
+      }
+    }
     CHECK(spmvMergeLaunch(w_val, A_t->d_spmv_tiles_[which], op, A_csrRowPtr,
-        A_csrColInd, A_csrVal, u_t->d_val_, A_nrows, A->nvals_, desc));
+        gather_ci, A_csrVal, gather_u, A_nrows, A->nvals_, desc));
 
     if (use_mask) {
       Storage mask_vec_type;

@@ -75,3 +75,34 @@ def test_edge_share_check_does_not_change_results(gb):
     want, wp = orc.vxm(int(sem), rp, ci, val, uu, u_present=up)
     assert np.array_equal(out[0], want != 0)
     assert np.array_equal(out[1], want != 0)
+
+
+@pytest.mark.parametrize("name", ["PlusMultiplies", "MinimumPlus"])
+def test_column_relabelling_is_bit_identical(gb, name):
+    """GB200_SPMV_RELABEL=1 (experimental, off by default): the generic pull SpMV
+    gathers through relabelled column indices from a permuted copy of u; products
+    and their order are unchanged, so the result must not differ in a single bit
+    (random float values on purpose)."""
+    import os
+    rp, ci = orc.rmat_csr(12)
+    n = len(rp) - 1
+    rng = np.random.RandomState(9)
+    val = rng.rand(len(ci)).astype(np.float32) + 0.5
+    u_h = rng.rand(n).astype(np.float32) + 0.5
+    sem = getattr(gb.Semiring, name)
+    out = {}
+    for flag in ("0", "1", "1"):                   # second "1" reuses the cached copy
+        os.environ["GB200_SPMV_RELABEL"] = flag
+        try:
+            A = make_matrix(gb, rp, ci, val, symmetric=False)
+            desc = gb.Descriptor(mxvmode=2)
+            u = gb.Vector(n)
+            u.build(u_h)
+            w = gb.Vector(n)
+            gb.vxm(w, None, None, sem, u, A, desc)
+            gb.vxm(w, None, None, sem, u, A, desc)
+            out.setdefault(flag, []).append(w.extractTuples().copy())
+        finally:
+            os.environ["GB200_SPMV_RELABEL"] = "0"
+    assert np.array_equal(out["0"][0].view(np.uint32), out["1"][0].view(np.uint32))
+    assert np.array_equal(out["0"][0].view(np.uint32), out["1"][1].view(np.uint32))
