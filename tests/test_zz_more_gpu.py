@@ -7,7 +7,13 @@ import pytest
 import oracle_binding as orc
 from test_parity_gpu import make_matrix, ragged_graph
 
-pytestmark = pytest.mark.gpu
+# Non-strict xfail until their first run on a device has been looked at: a pass is
+# reported as XPASS, a failure as XFAIL, and the suite's verdict stays what the
+# verified tests say.  (r02: drop the mark once these show XPASS.)
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False,
+                                reason="written after the r01 GPU budget was spent; "
+                                       "never executed on a device yet")]
 
 
 @pytest.fixture(scope="module")
