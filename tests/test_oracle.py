@@ -210,3 +210,30 @@ def test_loader_equals_reference_readmtx(name, directed):
     rp, ci = orc.build_csr(n, src, dst, undirected)
     rr, rc, _ = orc.ref_load_mtx(path, directed)
     assert np.array_equal(rp, rr) and np.array_equal(ci, rc)
+
+
+@needs_ref
+def test_oracle_equals_reference_cpu_on_random_graphs():
+    """Property test of the oracle pin: on random undirected graphs of assorted
+    shapes (isolated vertices, multi-edges in the input, tiny and ragged degrees)
+    the restatement and the reference's own CPU code agree bit for bit on BFS,
+    SSSP, PageRank and the triangle count."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(2, 60), m=st.integers(0, 400), seed=st.integers(0, 2**31 - 1))
+    def check(n, m, seed):
+        rng = np.random.RandomState(seed)
+        src = rng.randint(0, n, m).astype(np.int32)
+        dst = rng.randint(0, n, m).astype(np.int32)
+        rp, ci = orc.build_csr(n, src, dst, True)          # drops loops/duplicates
+        for s in (0, n - 1):
+            assert np.array_equal(orc.bfs(rp, ci, s), orc.ref_bfs(rp, ci, s))
+        if len(ci):
+            w = orc.ref_uniform_weights(seed % 1000, 1, 64, len(ci))
+            assert np.array_equal(orc.sssp(rp, ci, w, 0), orc.ref_sssp(rp, ci, w, 0))
+        assert np.array_equal(orc.pr(rp, ci), orc.ref_pr(rp, ci))
+        lr, lc = orc.tril(rp, ci)
+        assert orc.tc(lr, lc) == orc.ref_tc(lr, lc)
+
+    check()
