@@ -16,12 +16,8 @@ namespace backend {
 
 template <typename U, typename W, typename M,
           typename BinaryOpT, typename UnaryOpT>
-Info applyDense(DenseVector<W>*  w,
-                const Vector<M>* mask,
-                BinaryOpT        accum,
-                UnaryOpT         op,
-                DenseVector<U>*  u,
-                Descriptor*      desc) {
+Info applyDense(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, UnaryOpT op,
+    DenseVector<U>* u, Descriptor* desc) {
   std::cout << "DeVec Apply\n";
   std::cout << "Error: Feature not implemented yet!\n";
   return GrB_SUCCESS;
@@ -29,12 +25,8 @@ Info applyDense(DenseVector<W>*  w,
 
 template <typename U, typename W, typename M,
           typename BinaryOpT, typename UnaryOpT>
-Info applySparse(SparseVector<W>* w,
-                 const Vector<M>* mask,
-                 BinaryOpT        accum,
-                 UnaryOpT         op,
-                 SparseVector<U>* u,
-                 Descriptor*      desc) {
+Info applySparse(SparseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    UnaryOpT op, SparseVector<U>* u, Descriptor* desc) {
   std::cout << "SpVec Apply\n";
   std::cout << "Error: Feature not implemented yet!\n";
   return GrB_SUCCESS;
@@ -42,12 +34,8 @@ Info applySparse(SparseVector<W>* w,
 
 template <typename a, typename c, typename m,
           typename BinaryOpT, typename UnaryOpT>
-Info applyDense(DenseMatrix<c>*  C,
-                const Matrix<m>* mask,
-                BinaryOpT        accum,
-                UnaryOpT         op,
-                DenseMatrix<a>*  A,
-                Descriptor*      desc) {
+Info applyDense(DenseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, UnaryOpT op,
+    DenseMatrix<a>* A, Descriptor* desc) {
   std::cout << "DeMat Apply\n";
   std::cout << "Error: Feature not implemented yet!\n";
   return GrB_SUCCESS;
@@ -55,12 +43,8 @@ Info applyDense(DenseMatrix<c>*  C,
 
 template <typename a, typename c, typename m,
           typename BinaryOpT, typename UnaryOpT>
-Info applySparse(SparseMatrix<c>* C,
-                 const Matrix<m>* mask,
-                 BinaryOpT        accum,
-                 UnaryOpT         op,
-                 SparseMatrix<a>* A,
-                 Descriptor*      desc) {
+Info applySparse(SparseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum,
+    UnaryOpT op, SparseMatrix<a>* A, Descriptor* desc) {
   Desc_value backend;
   CHECK(desc->get(GrB_BACKEND, &backend));
 

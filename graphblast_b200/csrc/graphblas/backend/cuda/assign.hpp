@@ -20,13 +20,8 @@ namespace backend {
 
 template <typename W, typename T, typename M, typename I,
           typename BinaryOpT>
-Info assignDense(DenseVector<W>*  w,
-                 Vector<M>*       mask,
-                 BinaryOpT        accum,
-                 T                val,
-                 const Vector<I>* indices,
-                 Index            nindices,
-                 Descriptor*      desc) {
+Info assignDense(DenseVector<W>* w, Vector<M>* mask, BinaryOpT accum, T val,
+    const Vector<I>* indices, Index nindices, Descriptor* desc) {
   Desc_value scmp_mode, repl_mode;
   CHECK(desc->get(GrB_MASK, &scmp_mode));
   CHECK(desc->get(GrB_OUTP, &repl_mode));
@@ -108,13 +103,8 @@ Info assignDense(DenseVector<W>*  w,
 
 template <typename W, typename T, typename M,
           typename BinaryOpT>
-Info assignSparse(SparseVector<W>*     w,
-                  Vector<M>*           mask,
-                  BinaryOpT            accum,
-                  T                    val,
-                  const Vector<Index>* indices,
-                  Index                nindices,
-                  Descriptor*          desc) {
+Info assignSparse(SparseVector<W>* w, Vector<M>* mask, BinaryOpT accum, T val,
+    const Vector<Index>* indices, Index nindices, Descriptor* desc) {
   Desc_value scmp_mode;
   CHECK(desc->get(GrB_MASK, &scmp_mode));
   const bool use_scmp = (scmp_mode == GrB_SCMP);

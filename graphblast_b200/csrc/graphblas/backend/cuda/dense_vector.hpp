@@ -57,21 +57,14 @@ class DenseVector {
   inline Info nnz(Index* nnz_) const;
   Info computeNnz(Index* nnz, T identity, Descriptor* desc);
   template <typename BinaryOpT>
-  Info build(const std::vector<Index>* indices,
-             const std::vector<T>*     values,
-             Index                     nvals,
-             BinaryOpT                 dup);
-  Info build(const std::vector<T>* values,
-             Index                 nvals);
-  Info build(T*    values,
-             Index nvals);
+  Info build(const std::vector<Index>* indices, const std::vector<T>* values,
+      Index nvals, BinaryOpT dup);
+  Info build(const std::vector<T>* values, Index nvals);
+  Info build(T* values, Index nvals);
   Info setElement(T val, Index index);
   Info extractElement(T* val, Index index);
-  Info extractTuples(std::vector<Index>* indices,
-                     std::vector<T>*     values,
-                     Index*              n);
-  Info extractTuples(std::vector<T>* values,
-                     Index*          n);
+  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n);
+  Info extractTuples(std::vector<T>* values, Index* n);
   // Raw D2H copy into caller memory (C-ABI path; no std::vector in between).
   Info extractRaw(T* values, Index n);
 
@@ -277,17 +270,14 @@ Info DenseVector<T>::computeNnz(Index* nnz_t, T identity, Descriptor* desc) {
 template <typename T>
 template <typename BinaryOpT>
 Info DenseVector<T>::build(const std::vector<Index>* indices,
-                           const std::vector<T>*     values,
-                           Index                     nvals,
-                           BinaryOpT                 dup) {
+    const std::vector<T>* values, Index nvals, BinaryOpT dup) {
   std::cout << "DeVec Build Using Sparse Indices\n";
   std::cout << "Error: Feature not implemented yet!\n";
   return GrB_SUCCESS;
 }
 
 template <typename T>
-Info DenseVector<T>::build(const std::vector<T>* values,
-                           Index                 nvals) {
+Info DenseVector<T>::build(const std::vector<T>* values, Index nvals) {
   if (nvals > nvals_) return GrB_INDEX_OUT_OF_BOUNDS;
   CHECK(allocate());
   CHECK(gpuToCpu());
@@ -298,8 +288,7 @@ Info DenseVector<T>::build(const std::vector<T>* values,
 
 // Adopts a device pointer; ownership stays with the caller.
 template <typename T>
-Info DenseVector<T>::build(T*    values,
-                           Index nvals) {
+Info DenseVector<T>::build(T* values, Index nvals) {
   if (d_val_ != NULL && owns_device_) gbFree(d_val_);
   if (h_val_ != NULL && nvals != nvals_) { free(h_val_); h_val_ = NULL; }
   d_val_       = values;
@@ -322,8 +311,7 @@ Info DenseVector<T>::setElement(T val, Index index) {
   T* stage = reinterpret_cast<T*>(runtime().h_pinned);
   runtime().sync();              // staging slot may be in flight
   *stage = val;
-  CUDA_CALL(cudaMemcpyAsync(d_val_ + index, stage, sizeof(T),
-      cudaMemcpyHostToDevice, gbStream()));
+  CUDA_CALL(cudaMemcpyAsync(d_val_ + index, stage, sizeof(T), cudaMemcpyHostToDevice, gbStream()));
   runtime().sync();
   if (h_val_ != NULL && !need_update_) h_val_[index] = val;
   nnz_valid_ = false;
@@ -343,9 +331,8 @@ Info DenseVector<T>::extractElement(T* val, Index index) {
 }
 
 template <typename T>
-Info DenseVector<T>::extractTuples(std::vector<Index>* indices,
-                                   std::vector<T>*     values,
-                                   Index*              n) {
+Info DenseVector<T>::extractTuples(std::vector<Index>* indices, std::vector<T>* values,
+    Index* n) {
   std::cout << "DeVec ExtractTuples into Sparse Indices\n";
   std::cout << "Error: Feature not implemented yet!\n";
   return GrB_SUCCESS;
@@ -375,8 +362,7 @@ Info DenseVector<T>::extractRaw(T* values, Index n) {
   if (n < nvals_) return GrB_INSUFFICIENT_SPACE;
   CHECK(allocateGpu());
   CHECK(materialize());
-  CUDA_CALL(cudaMemcpyAsync(values, d_val_, static_cast<size_t>(n)*sizeof(T),
-      cudaMemcpyDeviceToHost, gbStream()));
+  CUDA_CALL(cudaMemcpyAsync(values, d_val_, static_cast<size_t>(n)*sizeof(T), cudaMemcpyDeviceToHost, gbStream()));
   runtime().sync();
   return GrB_SUCCESS;
 }
@@ -407,8 +393,7 @@ Info DenseVector<T>::resize(Index nsize) {
   CHECK(allocate());
   if (h_old != NULL) memcpy(h_val_, h_old, to_copy*sizeof(T));
   if (d_old != NULL)
-    CUDA_CALL(cudaMemcpyAsync(d_val_, d_old, to_copy*sizeof(T),
-        cudaMemcpyDeviceToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_val_, d_old, to_copy*sizeof(T), cudaMemcpyDeviceToDevice, gbStream()));
   if (h_old != NULL) free(h_old);
   if (d_old != NULL && old_owned) gbFree(d_old);
   nnz_valid_ = false;
@@ -431,8 +416,7 @@ Info DenseVector<T>::fill(T val) {
   zero_one_ = false;
   vals_stale_ = false;
   // bitmap shadow of a constant vector: all zero or all one
-  CUDA_CALL(cudaMemsetAsync(bitsStorage(), (val != static_cast<T>(0)) ? 0xff : 0,
-      bitWords()*sizeof(unsigned int), gbStream()));
+  CUDA_CALL(cudaMemsetAsync(bitsStorage(), (val != static_cast<T>(0)) ? 0xff : 0, bitWords()*sizeof(unsigned int), gbStream()));
   bits_valid_ = true;
   return GrB_SUCCESS;
 }
@@ -501,8 +485,7 @@ Info DenseVector<T>::allocate() {
 template <typename T>
 Info DenseVector<T>::cpuToGpu() {
   CHECK(allocate());
-  CUDA_CALL(cudaMemcpyAsync(d_val_, h_val_, static_cast<size_t>(nvals_)*sizeof(T),
-      cudaMemcpyHostToDevice, gbStream()));
+  CUDA_CALL(cudaMemcpyAsync(d_val_, h_val_, static_cast<size_t>(nvals_)*sizeof(T), cudaMemcpyHostToDevice, gbStream()));
   runtime().sync();
   need_update_ = false;
   nnz_valid_   = false;
@@ -519,9 +502,7 @@ Info DenseVector<T>::gpuToCpu(bool force_update) {
   CHECK(allocate());
   CHECK(materialize());
   if (need_update_ || force_update || fresh_host) {
-    CUDA_CALL(cudaMemcpyAsync(h_val_, d_val_,
-        static_cast<size_t>(nvals_)*sizeof(T), cudaMemcpyDeviceToHost,
-        gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(h_val_, d_val_, static_cast<size_t>(nvals_)*sizeof(T), cudaMemcpyDeviceToHost, gbStream()));
     runtime().sync();
   }
   need_update_ = false;

@@ -118,8 +118,7 @@ class Descriptor {
     const size_t bytes = (nblocks + 1)*sizeof(unsigned long long);
     if (bytes > slot_size_[GB_SCRATCH_LOOKBACK]) {
       void* p = scratch(GB_SCRATCH_LOOKBACK, bytes);
-      CUDA_CALL(cudaMemsetAsync(p, 0, slot_size_[GB_SCRATCH_LOOKBACK],
-          gbStream()));
+      CUDA_CALL(cudaMemsetAsync(p, 0, slot_size_[GB_SCRATCH_LOOKBACK], gbStream()));
       lookback_epoch_  = 0;
       lookback_ticket_ = 0;
     }
@@ -135,8 +134,7 @@ class Descriptor {
   unsigned long long* counters() {
     if (slot_ptr_[GB_SCRATCH_COUNTERS] == NULL) {
       void* p = scratch(GB_SCRATCH_COUNTERS, 64*sizeof(unsigned long long));
-      CUDA_CALL(cudaMemsetAsync(p, 0, slot_size_[GB_SCRATCH_COUNTERS],
-          gbStream()));
+      CUDA_CALL(cudaMemsetAsync(p, 0, slot_size_[GB_SCRATCH_COUNTERS], gbStream()));
     }
     return reinterpret_cast<unsigned long long*>(
         slot_ptr_[GB_SCRATCH_COUNTERS]);
@@ -239,8 +237,7 @@ inline Info Descriptor::resize(size_t target, std::string field) {
     void* fresh = NULL;
     CUDA_CALL(cudaMalloc(&fresh, target));
     if (*ptr != NULL) {
-      CUDA_CALL(cudaMemcpyAsync(fresh, *ptr, *size, cudaMemcpyDeviceToDevice,
-          gbStream()));
+      CUDA_CALL(cudaMemcpyAsync(fresh, *ptr, *size, cudaMemcpyDeviceToDevice, gbStream()));
       CUDA_CALL(cudaStreamSynchronize(gbStream()));
       CUDA_CALL(cudaFree(*ptr));
     }

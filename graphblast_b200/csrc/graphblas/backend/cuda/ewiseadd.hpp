@@ -23,13 +23,9 @@ namespace backend {
 // sparse (+) sparse -> dense: not implemented in the reference either (:18-27).
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAddInner(DenseVector<W>*        w,
-                   const Vector<M>*       mask,
-                   BinaryOpT              accum,
-                   SemiringT              op,
-                   const SparseVector<U>* u,
-                   const SparseVector<V>* v,
-                   Descriptor*            desc) {
+Info eWiseAddInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const SparseVector<U>* u, const SparseVector<V>* v,
+    Descriptor* desc) {
   std::cout << "Error: eWiseAdd sparse-sparse not implemented yet!\n";
   return GrB_SUCCESS;
 }
@@ -37,13 +33,8 @@ Info eWiseAddInner(DenseVector<W>*        w,
 // dense (+) dense
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAddInner(DenseVector<W>*       w,
-                   const Vector<M>*      mask,
-                   BinaryOpT             accum,
-                   SemiringT             op,
-                   const DenseVector<U>* u,
-                   const DenseVector<V>* v,
-                   Descriptor*           desc) {
+Info eWiseAddInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const DenseVector<U>* u, const DenseVector<V>* v, Descriptor* desc) {
   if (mask != NULL) {
     std::cout << "Error: Masked eWiseAdd dense-dense not implemented yet!\n";
     return GrB_SUCCESS;
@@ -63,14 +54,9 @@ Info eWiseAddInner(DenseVector<W>*       w,
 // sparse (+) dense; reverse == true when the dense operand was the first argument
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAddInner(DenseVector<W>*        w,
-                   const Vector<M>*       mask,
-                   BinaryOpT              accum,
-                   SemiringT              op,
-                   const SparseVector<U>* u,
-                   const DenseVector<V>*  v,
-                   bool                   reverse,
-                   Descriptor*            desc) {
+Info eWiseAddInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const SparseVector<U>* u, const DenseVector<V>* v, bool reverse,
+    Descriptor* desc) {
   if (mask != NULL) {
     std::cout << "Error: Masked eWiseAdd sparse-dense not implemented yet!\n";
     return GrB_SUCCESS;
@@ -102,13 +88,8 @@ Info eWiseAddInner(DenseVector<W>*        w,
 // sparse (+) scalar
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAddInner(DenseVector<W>*        w,
-                   const Vector<M>*       mask,
-                   BinaryOpT              accum,
-                   SemiringT              op,
-                   const SparseVector<U>* u,
-                   V                      val,
-                   Descriptor*            desc) {
+Info eWiseAddInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const SparseVector<U>* u, V val, Descriptor* desc) {
   if (mask != NULL) {
     std::cout << "eWiseAdd Sparse Vector Broadcast Scalar with Mask\n";
     std::cout << "Error: Feature not implemented yet!\n";
@@ -130,13 +111,8 @@ Info eWiseAddInner(DenseVector<W>*        w,
 // dense (+) scalar
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAddInner(DenseVector<W>*       w,
-                   const Vector<M>*      mask,
-                   BinaryOpT             accum,
-                   SemiringT             op,
-                   const DenseVector<U>* u,
-                   V                     val,
-                   Descriptor*           desc) {
+Info eWiseAddInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const DenseVector<U>* u, V val, Descriptor* desc) {
   if (mask != NULL) {
     std::cout << "eWiseAdd Dense Vector Broadcast Scalar with Mask\n";
     std::cout << "Error: Feature not implemented yet!\n";

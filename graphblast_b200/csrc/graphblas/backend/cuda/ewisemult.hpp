@@ -21,9 +21,8 @@ namespace backend {
 // In a sparse result, entries whose dense mask is 0 are set to identity
 // (reference zeroDenseIdentityKernel, kernels/util.hpp:34-50).
 template <typename W, typename M>
-__global__ void zeroWhereMaskZeroKernel(const M* mask, W identity,
-                                        const Index* w_ind, W* w_val,
-                                        Index nvals) {
+__global__ void zeroWhereMaskZeroKernel(const M* mask, W identity, const Index* w_ind,
+    W* w_val, Index nvals) {
   Index k = blockIdx.x*blockDim.x + threadIdx.x;
   const Index stride = gridDim.x*blockDim.x;
   for (; k < nvals; k += stride)
@@ -33,13 +32,8 @@ __global__ void zeroWhereMaskZeroKernel(const M* mask, W identity,
 // dense (x) dense -> dense (no mask, or dense mask)
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMultInner(DenseVector<W>*       w,
-                    const Vector<M>*      mask,
-                    BinaryOpT             accum,
-                    SemiringT             op,
-                    const DenseVector<U>* u,
-                    const DenseVector<V>* v,
-                    Descriptor*           desc) {
+Info eWiseMultInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const DenseVector<U>* u, const DenseVector<V>* v, Descriptor* desc) {
   Index n;
   u->nvals(&n);
   CHECK(w->allocateGpu());
@@ -60,13 +54,8 @@ Info eWiseMultInner(DenseVector<W>*       w,
 // dense (x) dense under a sparse mask -> sparse with the mask's pattern
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMultInner(SparseVector<W>*       w,
-                    const SparseVector<M>* mask,
-                    BinaryOpT              accum,
-                    SemiringT              op,
-                    const DenseVector<U>*  u,
-                    const DenseVector<V>*  v,
-                    Descriptor*            desc) {
+Info eWiseMultInner(SparseVector<W>* w, const SparseVector<M>* mask, BinaryOpT accum,
+    SemiringT op, const DenseVector<U>* u, const DenseVector<V>* v, Descriptor* desc) {
   Index mask_nvals;
   mask->nvals(&mask_nvals);
   CHECK(w->allocateGpu());
@@ -84,14 +73,9 @@ Info eWiseMultInner(SparseVector<W>*       w,
 // sparse (x) dense -> sparse with u's pattern; reverse swaps the mul arguments
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMultInner(SparseVector<W>*       w,
-                    const Vector<M>*       mask,
-                    BinaryOpT              accum,
-                    SemiringT              op,
-                    const SparseVector<U>* u,
-                    const DenseVector<V>*  v,
-                    bool                   reverse,
-                    Descriptor*            desc) {
+Info eWiseMultInner(SparseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const SparseVector<U>* u, const DenseVector<V>* v, bool reverse,
+    Descriptor* desc) {
   Storage mask_type = GrB_UNKNOWN;
   if (mask != NULL) mask->getStorage(&mask_type);
   if (mask != NULL && mask_type == GrB_SPARSE) {
@@ -123,13 +107,8 @@ Info eWiseMultInner(SparseVector<W>*       w,
 // sparse matrix (x) scalar: both value arrays are scaled (reference :275-341)
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMultInner(SparseMatrix<c>*       C,
-                    const Matrix<m>*       mask,
-                    BinaryOpT              accum,
-                    SemiringT              op,
-                    const SparseMatrix<a>* A,
-                    b                      val,
-                    Descriptor*            desc) {
+Info eWiseMultInner(SparseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum,
+    SemiringT op, const SparseMatrix<a>* A, b val, Descriptor* desc) {
   if (mask != NULL) {
     std::cout << "eWiseMult Sparse Matrix Broadcast Scalar with Mask\n";
     std::cout << "Error: Feature not implemented yet!\n";
@@ -159,13 +138,8 @@ Info eWiseMultInner(SparseMatrix<c>*       C,
 // sparse matrix (x) column vector: C(i,j) = mul(A(i,j), b[i])  (reference :470-545)
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMultColInner(SparseMatrix<c>*       C,
-                       const Matrix<m>*       mask,
-                       BinaryOpT              accum,
-                       SemiringT              op,
-                       const SparseMatrix<a>* A,
-                       const DenseVector<b>*  B,
-                       Descriptor*            desc) {
+Info eWiseMultColInner(SparseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum,
+    SemiringT op, const SparseMatrix<a>* A, const DenseVector<b>* B, Descriptor* desc) {
   if (mask != NULL) {
     std::cout << "eWiseMult Sparse Matrix Broadcast Col Vector with Mask\n";
     std::cout << "Error: Feature not implemented yet!\n";
@@ -198,13 +172,8 @@ Info eWiseMultColInner(SparseMatrix<c>*       C,
 // sparse matrix (x) row vector: C(i,j) = mul(A(i,j), b[j])  (reference :547-618)
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMultRowInner(SparseMatrix<c>*       C,
-                       const Matrix<m>*       mask,
-                       BinaryOpT              accum,
-                       SemiringT              op,
-                       const SparseMatrix<a>* A,
-                       const DenseVector<b>*  B,
-                       Descriptor*            desc) {
+Info eWiseMultRowInner(SparseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum,
+    SemiringT op, const SparseMatrix<a>* A, const DenseVector<b>* B, Descriptor* desc) {
   if (mask != NULL) {
     std::cout << "eWiseMult Sparse Matrix Broadcast Row Vector with Mask\n";
     std::cout << "Error: Feature not implemented yet!\n";

@@ -76,11 +76,8 @@ class Matrix {
 
   template <typename BinaryOpT>
   Info build(const std::vector<Index>* row_indices,
-             const std::vector<Index>* col_indices,
-             const std::vector<T>*     values,
-             Index                     nvals,
-             BinaryOpT                 dup,
-             char*                     dat_name) {
+      const std::vector<Index>* col_indices, const std::vector<T>* values, Index nvals,
+      BinaryOpT dup, char* dat_name) {
     mat_type_ = GrB_SPARSE;
     if (sparse_.nvals_ > 0) sparse_.clear();
     return sparse_.build(row_indices, col_indices, values, nvals, dup,
@@ -113,10 +110,8 @@ class Matrix {
     return GrB_UNINITIALIZED_OBJECT;
   }
 
-  Info extractTuples(std::vector<Index>* row_indices,
-                     std::vector<Index>* col_indices,
-                     std::vector<T>*     values,
-                     Index*              n) {
+  Info extractTuples(std::vector<Index>* row_indices, std::vector<Index>* col_indices,
+      std::vector<T>* values, Index* n) {
     if (isSparse())
       return sparse_.extractTuples(row_indices, col_indices, values, n);
     return GrB_UNINITIALIZED_OBJECT;

@@ -37,13 +37,8 @@ namespace backend {
 
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info mxm(Matrix<c>*       C,
-         const Matrix<m>* mask,
-         BinaryOpT        accum,
-         SemiringT        op,
-         const Matrix<a>* A,
-         const Matrix<b>* B,
-         Descriptor*      desc) {
+Info mxm(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
+    const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
   Storage A_mat_type;
   Storage B_mat_type;
   CHECK(A->getStorage(&A_mat_type));
@@ -52,8 +47,7 @@ Info mxm(Matrix<c>*       C,
   if (A_mat_type == GrB_SPARSE && B_mat_type == GrB_SPARSE) {
     CHECK(C->setStorage(GrB_SPARSE));
     if (mask) {
-      CHECK(spgemmMasked(&C->sparse_, mask, accum, op, &A->sparse_, &B->sparse_,
-          desc));
+      CHECK(spgemmMasked(&C->sparse_, mask, accum, op, &A->sparse_, &B->sparse_, desc));
     } else {
       std::cout << "Error: Unmasked SpGEMM not implemented yet!\n";
       return GrB_NOT_IMPLEMENTED;
@@ -68,13 +62,8 @@ Info mxm(Matrix<c>*       C,
 // Shared body of vxm / mxv once the descriptor says which side is transposed.
 template <bool IsVxm, typename W, typename U, typename a, typename M,
           typename BinaryOpT, typename SemiringT>
-Info mxvDispatch(Vector<W>*       w,
-                 const Vector<M>* mask,
-                 BinaryOpT        accum,
-                 SemiringT        op,
-                 const Matrix<a>* A,
-                 const Vector<U>* u,
-                 Descriptor*      desc) {
+Info mxvDispatch(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const Matrix<a>* A, const Vector<U>* u, Descriptor* desc) {
   Vector<U>* u_t = const_cast<Vector<U>*>(u);
 
   Storage u_vec_type;
@@ -120,8 +109,8 @@ Info mxvDispatch(Vector<W>*       w,
       bool prefer_pull = false;
       const bool may_switch = (mxv_mode == GrB_PUSHPULL) &&
           (A_symmetric || A_format == GrB_SPARSE_MATRIX_CSRCSC);
-      CHECK(spmspvMerge(&w->sparse_, mask, accum, op, &A->sparse_,
-          &u->sparse_, desc, may_switch ? &prefer_pull : NULL));
+      CHECK(spmspvMerge(&w->sparse_, mask, accum, op,
+          &A->sparse_, &u->sparse_, desc, may_switch ? &prefer_pull : NULL));
       if (prefer_pull) {
         CHECK(u_t->sparse2dense(op.identity(), desc));
         run_pull = true;
@@ -153,13 +142,8 @@ Info mxvDispatch(Vector<W>*       w,
 
 template <typename W, typename U, typename a, typename M,
           typename BinaryOpT, typename SemiringT>
-Info vxm(Vector<W>*       w,
-         const Vector<M>* mask,
-         BinaryOpT        accum,
-         SemiringT        op,
-         const Vector<U>* u,
-         const Matrix<a>* A,
-         Descriptor*      desc) {
+Info vxm(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const Vector<U>* u, const Matrix<a>* A, Descriptor* desc) {
   if (desc->debug()) {
     std::cout << "===Begin vxm===\n";
     CHECK(const_cast<Vector<U>*>(u)->print());
@@ -184,13 +168,8 @@ Info vxm(Vector<W>*       w,
 
 template <typename W, typename a, typename U, typename M,
           typename BinaryOpT, typename SemiringT>
-Info mxv(Vector<W>*       w,
-         const Vector<M>* mask,
-         BinaryOpT        accum,
-         SemiringT        op,
-         const Matrix<a>* A,
-         const Vector<U>* u,
-         Descriptor*      desc) {
+Info mxv(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const Matrix<a>* A, const Vector<U>* u, Descriptor* desc) {
   if (desc->debug()) {
     std::cout << "===Begin mxv===\n";
     CHECK(const_cast<Vector<U>*>(u)->print());
@@ -211,13 +190,8 @@ Info mxv(Vector<W>*       w,
 
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Vector<W>*       w,
-               const Vector<M>* mask,
-               BinaryOpT        accum,
-               SemiringT        op,
-               const Vector<U>* u,
-               const Vector<V>* v,
-               Descriptor*      desc) {
+Info eWiseMult(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const Vector<U>* u, const Vector<V>* v, Descriptor* desc) {
   Vector<V>* v_t = const_cast<Vector<V>*>(v);
   CHECK(u->materialize());
   CHECK(v->materialize());
@@ -241,28 +215,27 @@ Info eWiseMult(Vector<W>*       w,
       CHECK(mask->getStorage(&mask_type));
       if (mask_type == GrB_DENSE) {
         CHECK(w->setStorage(GrB_DENSE));
-        CHECK(eWiseMultInner(&w->dense_, mask, accum, op, &u->dense_,
-            &v->dense_, desc));
+        CHECK(eWiseMultInner(&w->dense_, mask, accum, op,
+            &u->dense_, &v->dense_, desc));
       } else if (mask_type == GrB_SPARSE) {
         CHECK(w->setStorage(GrB_SPARSE));
-        CHECK(eWiseMultInner(&w->sparse_, &mask->sparse_, accum, op,
-            &u->dense_, &v->dense_, desc));
+        CHECK(eWiseMultInner(&w->sparse_,
+            &mask->sparse_, accum, op, &u->dense_, &v->dense_, desc));
       } else {
         return GrB_INVALID_OBJECT;
       }
     } else {
       CHECK(w->setStorage(GrB_DENSE));
-      CHECK(eWiseMultInner(&w->dense_, mask, accum, op, &u->dense_,
-          &v->dense_, desc));
+      CHECK(eWiseMultInner(&w->dense_, mask, accum, op, &u->dense_, &v->dense_, desc));
     }
   } else if (u_vec_type == GrB_SPARSE && v_vec_type == GrB_DENSE) {
     CHECK(w->setStorage(GrB_SPARSE));
-    CHECK(eWiseMultInner(&w->sparse_, mask, accum, op, &u->sparse_,
-        &v->dense_, false, desc));
+    CHECK(eWiseMultInner(&w->sparse_, mask, accum, op,
+        &u->sparse_, &v->dense_, false, desc));
   } else if (u_vec_type == GrB_DENSE && v_vec_type == GrB_SPARSE) {
     CHECK(w->setStorage(GrB_SPARSE));
-    CHECK(eWiseMultInner(&w->sparse_, mask, accum, op, &v->sparse_,
-        &u->dense_, true, desc));
+    CHECK(eWiseMultInner(&w->sparse_, mask, accum, op,
+        &v->sparse_, &u->dense_, true, desc));
   } else {
     return GrB_INVALID_OBJECT;
   }
@@ -271,13 +244,8 @@ Info eWiseMult(Vector<W>*       w,
 
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Matrix<c>*       C,
-               const Matrix<m>* mask,
-               BinaryOpT        accum,
-               SemiringT        op,
-               const Matrix<a>* A,
-               const Matrix<b>* B,
-               Descriptor*      desc) {
+Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
+    const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
   std::cout << "Error: eWiseMult matrix variant not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
@@ -285,13 +253,8 @@ Info eWiseMult(Matrix<c>*       C,
 // Extension: matrix (x) broadcast scalar
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Matrix<c>*       C,
-               const Matrix<m>* mask,
-               BinaryOpT        accum,
-               SemiringT        op,
-               const Matrix<a>* A,
-               b                val,
-               Descriptor*      desc) {
+Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
+    const Matrix<a>* A, b val, Descriptor* desc) {
   Storage A_mat_type;
   CHECK(A->getStorage(&A_mat_type));
   if (A_mat_type != GrB_SPARSE) {
@@ -313,13 +276,8 @@ Info eWiseMult(Matrix<c>*       C,
 // GrB_INP1 is GrB_TRAN)
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Matrix<c>*       C,
-               const Matrix<m>* mask,
-               BinaryOpT        accum,
-               SemiringT        op,
-               const Matrix<a>* A,
-               const Vector<b>* B,
-               Descriptor*      desc) {
+Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
+    const Matrix<a>* A, const Vector<b>* B, Descriptor* desc) {
   Desc_value inp0_mode, inp1_mode;
   CHECK(desc->get(GrB_INP0, &inp0_mode));
   CHECK(desc->get(GrB_INP1, &inp1_mode));
@@ -348,23 +306,18 @@ Info eWiseMult(Matrix<c>*       C,
     return GrB_NOT_IMPLEMENTED;
   }
   if (inp1_mode != GrB_TRAN)
-    CHECK(eWiseMultColInner(&C->sparse_, mask, accum, op, &A->sparse_,
-        &B->dense_, desc));
+    CHECK(eWiseMultColInner(&C->sparse_, mask, accum, op,
+        &A->sparse_, &B->dense_, desc));
   else
-    CHECK(eWiseMultRowInner(&C->sparse_, mask, accum, op, &A->sparse_,
-        &B->dense_, desc));
+    CHECK(eWiseMultRowInner(&C->sparse_, mask, accum, op,
+        &A->sparse_, &B->dense_, desc));
   return GrB_SUCCESS;
 }
 
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAdd(Vector<W>*       w,
-              const Vector<M>* mask,
-              BinaryOpT        accum,
-              SemiringT        op,
-              const Vector<U>* u,
-              const Vector<V>* v,
-              Descriptor*      desc) {
+Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const Vector<U>* u, const Vector<V>* v, Descriptor* desc) {
   Vector<U>* u_t = const_cast<Vector<U>*>(u);
   Vector<V>* v_t = const_cast<Vector<V>*>(v);
   CHECK(u->materialize());
@@ -390,17 +343,15 @@ Info eWiseAdd(Vector<W>*       w,
 
   CHECK(w->setStorage(GrB_DENSE));
   if (u_vec_type == GrB_SPARSE && v_vec_type == GrB_SPARSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_,
-        &v->sparse_, desc));
+    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_, &v->sparse_, desc));
   } else if (u_vec_type == GrB_DENSE && v_vec_type == GrB_DENSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->dense_,
-        &v->dense_, desc));
+    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->dense_, &v->dense_, desc));
   } else if (u_vec_type == GrB_SPARSE && v_vec_type == GrB_DENSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_,
-        &v->dense_, false, desc));
+    CHECK(eWiseAddInner(&w->dense_, mask, accum, op,
+        &u->sparse_, &v->dense_, false, desc));
   } else if (u_vec_type == GrB_DENSE && v_vec_type == GrB_SPARSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &v->sparse_,
-        &u->dense_, true, desc));
+    CHECK(eWiseAddInner(&w->dense_, mask, accum, op,
+        &v->sparse_, &u->dense_, true, desc));
   } else {
     std::cout << "Error: eWiseAdd backend invalid choice!\n";
     return GrB_INVALID_OBJECT;
@@ -410,13 +361,8 @@ Info eWiseAdd(Vector<W>*       w,
 
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAdd(Matrix<c>*       C,
-              const Matrix<m>* mask,
-              BinaryOpT        accum,
-              SemiringT        op,
-              const Matrix<a>* A,
-              const Matrix<b>* B,
-              Descriptor*      desc) {
+Info eWiseAdd(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
+    const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
   std::cout << "Error: eWiseAdd matrix variant not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
@@ -424,13 +370,8 @@ Info eWiseAdd(Matrix<c>*       C,
 // Extension: vector (+) broadcast scalar
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
-Info eWiseAdd(Vector<W>*       w,
-              const Vector<M>* mask,
-              BinaryOpT        accum,
-              SemiringT        op,
-              const Vector<U>* u,
-              V                val,
-              Descriptor*      desc) {
+Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const Vector<U>* u, V val, Descriptor* desc) {
   CHECK(u->materialize());
   CHECK(w->materialize());
   Storage u_vec_type;
@@ -452,26 +393,16 @@ Info eWiseAdd(Vector<W>*       w,
 
 template <typename W, typename U, typename M,
           typename BinaryOpT>
-Info extract(Vector<W>*                w,
-             const Vector<M>*          mask,
-             BinaryOpT                 accum,
-             const Vector<U>*          u,
-             const std::vector<Index>* indices,
-             Index                     nindices,
-             Descriptor*               desc) {
+Info extract(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, const Vector<U>* u,
+    const std::vector<Index>* indices, Index nindices, Descriptor* desc) {
   std::cout << "Error: extract vector variant not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
 
 template <typename W, typename U, typename M,
           typename BinaryOpT>
-Info assignIndexed(Vector<W>*       w,
-                   const Vector<M>* mask,
-                   BinaryOpT        accum,
-                   const Vector<U>* u,
-                   int*             indices,
-                   Index            nindices,
-                   Descriptor*      desc) {
+Info assignIndexed(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    const Vector<U>* u, int* indices, Index nindices, Descriptor* desc) {
   std::cout << "Error: assignIndexed not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
@@ -479,13 +410,8 @@ Info assignIndexed(Vector<W>*       w,
 // Masked constant assign
 template <typename W, typename T, typename M,
           typename BinaryOpT>
-Info assign(Vector<W>*           w,
-            Vector<M>*           mask,
-            BinaryOpT            accum,
-            T                    val,
-            const Vector<Index>* indices,
-            Index                nindices,
-            Descriptor*          desc) {
+Info assign(Vector<W>* w, Vector<M>* mask, BinaryOpT accum, T val,
+    const Vector<Index>* indices, Index nindices, Descriptor* desc) {
   if (desc->debug()) {
     std::cout << "===Begin assign===\n";
     std::cout << "Input: " << val << std::endl;
@@ -500,11 +426,9 @@ Info assign(Vector<W>*           w,
   if (vec_type == GrB_SPARSE && mask != NULL) CHECK(mask->materialize());
 
   if (vec_type == GrB_SPARSE) {
-    CHECK(assignSparse(&w->sparse_, mask, accum, val, indices, nindices,
-        desc));
+    CHECK(assignSparse(&w->sparse_, mask, accum, val, indices, nindices, desc));
   } else if (vec_type == GrB_DENSE) {
-    CHECK(assignDense(&w->dense_, mask, accum, val, indices, nindices,
-        desc));
+    CHECK(assignDense(&w->dense_, mask, accum, val, indices, nindices, desc));
   }
 
   if (desc->debug()) {
@@ -516,12 +440,8 @@ Info assign(Vector<W>*           w,
 
 template <typename W, typename U, typename M,
           typename BinaryOpT,     typename UnaryOpT>
-Info apply(Vector<W>*       w,
-           const Vector<M>* mask,
-           BinaryOpT        accum,
-           UnaryOpT         op,
-           const Vector<U>* u,
-           Descriptor*      desc) {
+Info apply(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, UnaryOpT op,
+    const Vector<U>* u, Descriptor* desc) {
   Vector<U>* u_t = const_cast<Vector<U>*>(u);
   CHECK(u->materialize());
   CHECK(w->materialize());
@@ -542,12 +462,8 @@ Info apply(Vector<W>*       w,
 
 template <typename c, typename a, typename m,
           typename BinaryOpT,     typename UnaryOpT>
-Info apply(Matrix<c>*       C,
-           const Matrix<m>* mask,
-           BinaryOpT        accum,
-           UnaryOpT         op,
-           const Matrix<a>* A,
-           Descriptor*      desc) {
+Info apply(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, UnaryOpT op,
+    const Matrix<a>* A, Descriptor* desc) {
   Matrix<a>* A_t = const_cast<Matrix<a>*>(A);
   Storage A_mat_type;
   CHECK(A->getStorage(&A_mat_type));
@@ -566,12 +482,8 @@ Info apply(Matrix<c>*       C,
 // matrix rows -> vector
 template <typename W, typename a, typename M,
           typename BinaryOpT,     typename MonoidT>
-Info reduce(Vector<W>*       w,
-            const Vector<M>* mask,
-            BinaryOpT        accum,
-            MonoidT          op,
-            const Matrix<a>* A,
-            Descriptor*      desc) {
+Info reduce(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
+    const Matrix<a>* A, Descriptor* desc) {
   Storage mat_type;
   CHECK(A->getStorage(&mat_type));
   CHECK(w->setStorage(GrB_DENSE));
@@ -592,11 +504,7 @@ Info reduce(Vector<W>*       w,
 // vector -> scalar
 template <typename T, typename U,
           typename BinaryOpT, typename MonoidT>
-Info reduce(T*               val,
-            BinaryOpT        accum,
-            MonoidT          op,
-            const Vector<U>* u,
-            Descriptor*      desc) {
+Info reduce(T* val, BinaryOpT accum, MonoidT op, const Vector<U>* u, Descriptor* desc) {
   Storage vec_type;
   CHECK(u->getStorage(&vec_type));
 
@@ -615,11 +523,7 @@ Info reduce(T*               val,
 // matrix -> scalar
 template <typename T, typename a,
           typename BinaryOpT,     typename MonoidT>
-Info reduce(T*               val,
-            BinaryOpT        accum,
-            MonoidT          op,
-            const Matrix<a>* A,
-            Descriptor*      desc) {
+Info reduce(T* val, BinaryOpT accum, MonoidT op, const Matrix<a>* A, Descriptor* desc) {
   Storage mat_type;
   CHECK(A->getStorage(&mat_type));
 
@@ -637,11 +541,8 @@ Info reduce(T*               val,
 
 template <typename c, typename a, typename m,
           typename BinaryOpT>
-Info transpose(Matrix<c>*       C,
-               const Matrix<m>* mask,
-               BinaryOpT        accum,
-               const Matrix<a>* A,
-               Descriptor*      desc) {
+Info transpose(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, const Matrix<a>* A,
+    Descriptor* desc) {
   std::cout << "Error: transpose not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
@@ -650,74 +551,51 @@ Info transpose(Matrix<c>*       C,
 
 template <typename T, typename a, typename b,
           typename SemiringT>
-Info traceMxmTranspose(T*               val,
-                       SemiringT        op,
-                       const Matrix<a>* A,
-                       const Matrix<b>* B,
-                       Descriptor*      desc) {
+Info traceMxmTranspose(T* val, SemiringT op, const Matrix<a>* A, const Matrix<b>* B,
+    Descriptor* desc) {
   std::cout << "Error: Trace operator not implemented!\n";
   return GrB_NOT_IMPLEMENTED;
 }
 
 template <typename W, typename M, typename U, typename T>
-Info scatter(Vector<W>*       w,
-             const Vector<M>* mask,
-             const Vector<U>* u,
-             T                val,
-             Descriptor*      desc) {
+Info scatter(Vector<W>* w, const Vector<M>* mask, const Vector<U>* u, T val,
+    Descriptor* desc) {
   std::cout << "Error: scatter not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
 
 template <typename W, typename U, typename M, typename I,
           typename BinaryOpT>
-Info assignScatter(Vector<W>*       w,
-                   const Vector<M>* mask,
-                   BinaryOpT        accum,
-                   const Vector<U>* u,
-                   const Vector<I>* indices,
-                   Descriptor*      desc) {
+Info assignScatter(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    const Vector<U>* u, const Vector<I>* indices, Descriptor* desc) {
   std::cout << "Error: assignScatter not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
 
 template <typename W, typename U, typename M, typename I,
           typename BinaryOpT>
-Info extractGather(Vector<W>*       w,
-                   const Vector<M>* mask,
-                   BinaryOpT        accum,
-                   const Vector<U>* u,
-                   const Vector<I>* indices,
-                   Descriptor*      desc) {
+Info extractGather(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    const Vector<U>* u, const Vector<I>* indices, Descriptor* desc) {
   std::cout << "Error: extractGather not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
 
 template <typename W, typename a>
-Info graphColor(Vector<W>*       w,
-                const Matrix<a>* A,
-                Descriptor*      desc) {
+Info graphColor(Vector<W>* w, const Matrix<a>* A, Descriptor* desc) {
   std::cout << "Error: graphColor (cuSPARSE csrcolor) not implemented!\n";
   return GrB_NOT_IMPLEMENTED;
 }
 
 template <typename W, typename U, typename a, typename M,
           typename BinaryOpT, typename SemiringT>
-Info applyVxm(Vector<W>*       w,
-              const Vector<M>* mask,
-              BinaryOpT        accum,
-              SemiringT        op,
-              const Vector<U>* u,
-              const Matrix<a>* A,
-              Descriptor*      desc) {
+Info applyVxm(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const Vector<U>* u, const Matrix<a>* A, Descriptor* desc) {
   std::cout << "Error: applyVxm not implemented yet!\n";
   return GrB_NOT_IMPLEMENTED;
 }
 
 template <typename c, typename a>
-Info tril(Matrix<c>*  C,
-          Matrix<a>*  A,
-          Descriptor* desc) {
+Info tril(Matrix<c>* C, Matrix<a>* A, Descriptor* desc) {
   Storage A_mat_type;
   CHECK(A->getStorage(&A_mat_type));
 

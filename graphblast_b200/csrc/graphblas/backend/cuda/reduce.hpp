@@ -18,12 +18,8 @@ namespace backend {
 
 template <typename T, typename U,
           typename BinaryOpT, typename MonoidT>
-Info reduceCommon(T*          val,
-                  BinaryOpT   accum,
-                  MonoidT     op,
-                  const U*    d_val,
-                  Index       nvals,
-                  Descriptor* desc) {
+Info reduceCommon(T* val, BinaryOpT accum, MonoidT op, const U* d_val, Index nvals,
+    Descriptor* desc) {
   if (nvals == 0) {
     *val = op.identity();
     return GrB_SUCCESS;
@@ -66,11 +62,8 @@ Info reduceCommon(T*          val,
 // Dense vector
 template <typename T, typename U,
           typename BinaryOpT, typename MonoidT>
-Info reduceInner(T*                     val,
-                 BinaryOpT              accum,
-                 MonoidT                op,
-                 const DenseVector<U>*  u,
-                 Descriptor*            desc) {
+Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const DenseVector<U>* u,
+    Descriptor* desc) {
   DenseVector<U>* u_t = const_cast<DenseVector<U>*>(u);
   // plus-like monoid over a 0/1 vector == number of ones.
   if (u_t->zero_one_ && op(3, 5) == 8 && op.identity() == static_cast<T>(0)) {
@@ -86,11 +79,8 @@ Info reduceInner(T*                     val,
 // Sparse vector
 template <typename T, typename U,
           typename BinaryOpT, typename MonoidT>
-Info reduceInner(T*                     val,
-                 BinaryOpT              accum,
-                 MonoidT                op,
-                 const SparseVector<U>* u,
-                 Descriptor*            desc) {
+Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const SparseVector<U>* u,
+    Descriptor* desc) {
   if (desc->struconly())
     *val = u->nvals_;
   else
@@ -101,11 +91,8 @@ Info reduceInner(T*                     val,
 // Sparse matrix -> scalar
 template <typename T, typename a,
           typename BinaryOpT, typename MonoidT>
-Info reduceInner(T*                     val,
-                 BinaryOpT              accum,
-                 MonoidT                op,
-                 const SparseMatrix<a>* A,
-                 Descriptor*            desc) {
+Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const SparseMatrix<a>* A,
+    Descriptor* desc) {
   if (desc->struconly())
     *val = A->nvals_;
   else
@@ -116,12 +103,8 @@ Info reduceInner(T*                     val,
 // Dense matrix -> vector: placeholder, as in the reference (:94-104)
 template <typename W, typename a, typename M,
           typename BinaryOpT,     typename MonoidT>
-Info reduceInner(DenseVector<W>*       w,
-                 const Vector<M>*      mask,
-                 BinaryOpT             accum,
-                 MonoidT               op,
-                 const DenseMatrix<a>* A,
-                 Descriptor*           desc) {
+Info reduceInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
+    const DenseMatrix<a>* A, Descriptor* desc) {
   std::cout << "Error: Dense reduce matrix-to-vector not implemented yet!\n";
   return GrB_SUCCESS;
 }
@@ -129,20 +112,15 @@ Info reduceInner(DenseVector<W>*       w,
 // Sparse matrix rows -> dense vector
 template <typename W, typename a, typename M,
           typename BinaryOpT,     typename MonoidT>
-Info reduceInner(DenseVector<W>*        w,
-                 const Vector<M>*       mask,
-                 BinaryOpT              accum,
-                 MonoidT                op,
-                 const SparseMatrix<a>* A,
-                 Descriptor*            desc) {
+Info reduceInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
+    const SparseMatrix<a>* A, Descriptor* desc) {
   if (desc->struconly()) {
     // The reference leaves w untouched here (:123-124).
   } else {
     if (A->nrows_ == 0) return GrB_INVALID_OBJECT;
     CHECK(w->allocateGpu());
     reduceRowsKernel<<<gridFor(static_cast<size_t>(A->nrows_)*32, 256), 256, 0,
-        gbStream()>>>(w->d_val_, A->d_csrRowPtr_, A->d_csrVal_, A->nrows_, op,
-        static_cast<W>(op.identity()));
+        gbStream()>>>(w->d_val_, A->d_csrRowPtr_, A->d_csrVal_, A->nrows_, op, static_cast<W>(op.identity()));
     GB_KERNEL_CHECK();
     w->touched();
     w->nnz_ = A->nrows_;
@@ -153,11 +131,8 @@ Info reduceInner(DenseVector<W>*        w,
 // Dense matrix -> scalar: placeholder, as in the reference (:147-156)
 template <typename T, typename a,
           typename BinaryOpT,     typename MonoidT>
-Info reduceInner(T*                    val,
-                 BinaryOpT             accum,
-                 MonoidT               op,
-                 const DenseMatrix<a>* A,
-                 Descriptor*           desc) {
+Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const DenseMatrix<a>* A,
+    Descriptor* desc) {
   std::cout << "Error: Dense reduce matrix-to-scalar not implemented yet!\n";
   return GrB_SUCCESS;
 }

@@ -49,31 +49,18 @@ class SparseMatrix {
   Info nvals(Index* nvals_t) const;
   template <typename BinaryOpT>
   Info build(const std::vector<Index>* row_indices,
-             const std::vector<Index>* col_indices,
-             const std::vector<T>*     values,
-             Index                     nvals,
-             BinaryOpT                 dup,
-             char*                     dat_name);
+      const std::vector<Index>* col_indices, const std::vector<T>* values, Index nvals,
+      BinaryOpT dup, char* dat_name);
   Info build(char* dat_name);
-  Info build(const std::vector<T>* values,
-             Index                 nvals);
-  Info build(Index* row_ptr,
-             Index* col_ind,
-             T*     values,
-             Index  nvals);
+  Info build(const std::vector<T>* values, Index nvals);
+  Info build(Index* row_ptr, Index* col_ind, T* values, Index nvals);
   // Device-resident CSC (or aliasing request) supplied by the caller.
   Info adoptCsc(Index* col_ptr, Index* row_ind, T* values, bool symmetric);
-  Info setElement(Index row_index,
-                  Index col_index);
-  Info extractElement(T*    val,
-                      Index row_index,
-                      Index col_index);
-  Info extractTuples(std::vector<Index>* row_indices,
-                     std::vector<Index>* col_indices,
-                     std::vector<T>*     values,
-                     Index*              n);
-  Info extractTuples(std::vector<T>* values,
-                     Index*          n);
+  Info setElement(Index row_index, Index col_index);
+  Info extractElement(T* val, Index row_index, Index col_index);
+  Info extractTuples(std::vector<Index>* row_indices, std::vector<Index>* col_indices,
+      std::vector<T>* values, Index* n);
+  Info extractTuples(std::vector<T>* values, Index* n);
 
   // Handy methods
   const T operator[](Index ind);
@@ -264,8 +251,8 @@ Info SparseMatrix<T>::dup(const SparseMatrix* rhs) {
 
   CHECK(allocateGpu());
   cudaStream_t s = gbStream();
-  CUDA_CALL(cudaMemcpyAsync(d_csrRowPtr_, rhs->d_csrRowPtr_,
-      (nrows_+1)*sizeof(Index), cudaMemcpyDeviceToDevice, s));
+  CUDA_CALL(cudaMemcpyAsync(d_csrRowPtr_, rhs->d_csrRowPtr_, (nrows_+1)*sizeof(Index),
+      cudaMemcpyDeviceToDevice, s));
   if (nvals_ > 0) {
     CUDA_CALL(cudaMemcpyAsync(d_csrColInd_, rhs->d_csrColInd_,
         static_cast<size_t>(nvals_)*sizeof(Index), cudaMemcpyDeviceToDevice, s));
@@ -281,8 +268,7 @@ Info SparseMatrix<T>::dup(const SparseMatrix* rhs) {
           (ncols_+1)*sizeof(Index), cudaMemcpyDeviceToDevice, s));
       if (nvals_ > 0)
         CUDA_CALL(cudaMemcpyAsync(d_cscRowInd_, rhs->d_cscRowInd_,
-            static_cast<size_t>(nvals_)*sizeof(Index),
-            cudaMemcpyDeviceToDevice, s));
+            static_cast<size_t>(nvals_)*sizeof(Index), cudaMemcpyDeviceToDevice, s));
     }
     csc_initialized_ = true;
   }
@@ -325,11 +311,8 @@ inline Info SparseMatrix<T>::nvals(Index* nvals_t) const {
 template <typename T>
 template <typename BinaryOpT>
 Info SparseMatrix<T>::build(const std::vector<Index>* row_indices,
-                            const std::vector<Index>* col_indices,
-                            const std::vector<T>*     values,
-                            Index                     nvals,
-                            BinaryOpT                 dup,
-                            char*                     dat_name) {
+    const std::vector<Index>* col_indices, const std::vector<T>* values, Index nvals,
+    BinaryOpT dup, char* dat_name) {
   freeHost();
   freeDevice();
   nvals_ = nvals;
@@ -338,8 +321,8 @@ Info SparseMatrix<T>::build(const std::vector<Index>* row_indices,
   if (dat_name != NULL)
     symmetric_ = (strstr(dat_name, ".ud.") != NULL);
 
-  coo2csr(h_csrRowPtr_, h_csrColInd_, h_csrVal_,
-          *row_indices, *col_indices, *values, nrows_, ncols_);
+  coo2csr(h_csrRowPtr_, h_csrColInd_, h_csrVal_, *row_indices, *col_indices, *values,
+      nrows_, ncols_);
 
   if (format_ == GrB_SPARSE_MATRIX_CSRONLY) {
     if (h_cscColPtr_ != NULL) free(h_cscColPtr_);
@@ -349,8 +332,8 @@ Info SparseMatrix<T>::build(const std::vector<Index>* row_indices,
     h_cscRowInd_ = h_csrColInd_;
     h_cscVal_    = h_csrVal_;
   } else {
-    coo2csc(h_cscColPtr_, h_cscRowInd_, h_cscVal_,
-            *row_indices, *col_indices, *values, nrows_, ncols_);
+    coo2csc(h_cscColPtr_, h_cscRowInd_, h_cscVal_, *row_indices, *col_indices, *values,
+        nrows_, ncols_);
     csc_initialized_ = true;
   }
   csr_initialized_ = true;
@@ -415,8 +398,8 @@ Info SparseMatrix<T>::build(char* dat_name) {
         h_cscRowInd_ = h_csrColInd_;
         h_cscVal_    = h_csrVal_;
       } else {
-        csr2csc(h_cscColPtr_, h_cscRowInd_, h_cscVal_,
-                h_csrRowPtr_, h_csrColInd_, h_csrVal_, nrows_, ncols_);
+        csr2csc(h_cscColPtr_, h_cscRowInd_, h_cscVal_, h_csrRowPtr_, h_csrColInd_,
+            h_csrVal_, nrows_, ncols_);
         csc_initialized_ = true;
       }
       csr_initialized_ = true;
@@ -431,8 +414,7 @@ Info SparseMatrix<T>::build(char* dat_name) {
 }
 
 template <typename T>
-Info SparseMatrix<T>::build(const std::vector<T>* values,
-                            Index                 nvals) {
+Info SparseMatrix<T>::build(const std::vector<T>* values, Index nvals) {
   std::cout << "SparseMatrix Build from dense input\n";
   std::cout << "Error: Feature not implemented yet!\n";
   return GrB_SUCCESS;
@@ -440,10 +422,7 @@ Info SparseMatrix<T>::build(const std::vector<T>* values,
 
 // Adopts DEVICE CSR arrays without taking ownership (reference :418-435).
 template <typename T>
-Info SparseMatrix<T>::build(Index* row_ptr,
-                            Index* col_ind,
-                            T*     values,
-                            Index  nvals) {
+Info SparseMatrix<T>::build(Index* row_ptr, Index* col_ind, T* values, Index nvals) {
   freeDevice();
   freeHost();
   d_csrRowPtr_ = row_ptr;
@@ -462,7 +441,7 @@ Info SparseMatrix<T>::build(Index* row_ptr,
 // when the values are symmetric, e.g. a pattern matrix).
 template <typename T>
 Info SparseMatrix<T>::adoptCsc(Index* col_ptr, Index* row_ind, T* values,
-                               bool symmetric) {
+    bool symmetric) {
   if (d_csrRowPtr_ == NULL) return GrB_UNINITIALIZED_OBJECT;
   dropSpmvTiles();
   symmetric_ = symmetric;
@@ -482,8 +461,7 @@ Info SparseMatrix<T>::adoptCsc(Index* col_ptr, Index* row_ind, T* values,
     // normalisation) must be able to make CSR and CSC values differ.
     const size_t nv = nvals_ > 0 ? nvals_ : 1;
     d_cscVal_ = reinterpret_cast<T*>(gbMalloc(nv*sizeof(T)));
-    CUDA_CALL(cudaMemcpyAsync(d_cscVal_, d_csrVal_, nv*sizeof(T),
-        cudaMemcpyDeviceToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_cscVal_, d_csrVal_, nv*sizeof(T), cudaMemcpyDeviceToDevice, gbStream()));
     cscval_ownership_ = true;
   }
   csc_initialized_ = true;
@@ -507,9 +485,7 @@ Info SparseMatrix<T>::extractElement(T* val, Index row_index, Index col_index) {
 
 template <typename T>
 Info SparseMatrix<T>::extractTuples(std::vector<Index>* row_indices,
-                                    std::vector<Index>* col_indices,
-                                    std::vector<T>*     values,
-                                    Index*              n) {
+    std::vector<Index>* col_indices, std::vector<T>* values, Index* n) {
   CHECK(gpuToCpu());
   row_indices->clear();
   col_indices->clear();
@@ -768,25 +744,19 @@ Info SparseMatrix<T>::cpuToGpu() {
   cudaStream_t s = gbStream();
   const size_t nv = nvals_;
 
-  CUDA_CALL(cudaMemcpyAsync(d_csrRowPtr_, h_csrRowPtr_,
-      (nrows_+1)*sizeof(Index), cudaMemcpyHostToDevice, s));
+  CUDA_CALL(cudaMemcpyAsync(d_csrRowPtr_, h_csrRowPtr_, (nrows_+1)*sizeof(Index), cudaMemcpyHostToDevice, s));
   if (nv > 0) {
-    CUDA_CALL(cudaMemcpyAsync(d_csrColInd_, h_csrColInd_, nv*sizeof(Index),
-        cudaMemcpyHostToDevice, s));
-    CUDA_CALL(cudaMemcpyAsync(d_csrVal_, h_csrVal_, nv*sizeof(T),
-        cudaMemcpyHostToDevice, s));
+    CUDA_CALL(cudaMemcpyAsync(d_csrColInd_, h_csrColInd_, nv*sizeof(Index), cudaMemcpyHostToDevice, s));
+    CUDA_CALL(cudaMemcpyAsync(d_csrVal_, h_csrVal_, nv*sizeof(T), cudaMemcpyHostToDevice, s));
   }
 
   if (format_ == GrB_SPARSE_MATRIX_CSRCSC) {
     if (nv > 0)
-      CUDA_CALL(cudaMemcpyAsync(d_cscVal_, h_cscVal_, nv*sizeof(T),
-          cudaMemcpyHostToDevice, s));
+      CUDA_CALL(cudaMemcpyAsync(d_cscVal_, h_cscVal_, nv*sizeof(T), cudaMemcpyHostToDevice, s));
     if (!symmetric_) {
-      CUDA_CALL(cudaMemcpyAsync(d_cscColPtr_, h_cscColPtr_,
-          (ncols_+1)*sizeof(Index), cudaMemcpyHostToDevice, s));
+      CUDA_CALL(cudaMemcpyAsync(d_cscColPtr_, h_cscColPtr_, (ncols_+1)*sizeof(Index), cudaMemcpyHostToDevice, s));
       if (nv > 0)
-        CUDA_CALL(cudaMemcpyAsync(d_cscRowInd_, h_cscRowInd_, nv*sizeof(Index),
-            cudaMemcpyHostToDevice, s));
+        CUDA_CALL(cudaMemcpyAsync(d_cscRowInd_, h_cscRowInd_, nv*sizeof(Index), cudaMemcpyHostToDevice, s));
     } else {
       d_cscColPtr_ = d_csrRowPtr_;
       d_cscRowInd_ = d_csrColInd_;
@@ -804,25 +774,19 @@ Info SparseMatrix<T>::gpuToCpu(bool force_update) {
   if ((need_update_ || force_update || fresh_host) && d_csrRowPtr_ != NULL) {
     cudaStream_t s = gbStream();
     const size_t nv = nvals_;
-    CUDA_CALL(cudaMemcpyAsync(h_csrRowPtr_, d_csrRowPtr_,
-        (nrows_+1)*sizeof(Index), cudaMemcpyDeviceToHost, s));
+    CUDA_CALL(cudaMemcpyAsync(h_csrRowPtr_, d_csrRowPtr_, (nrows_+1)*sizeof(Index), cudaMemcpyDeviceToHost, s));
     if (nv > 0) {
-      CUDA_CALL(cudaMemcpyAsync(h_csrColInd_, d_csrColInd_, nv*sizeof(Index),
-          cudaMemcpyDeviceToHost, s));
-      CUDA_CALL(cudaMemcpyAsync(h_csrVal_, d_csrVal_, nv*sizeof(T),
-          cudaMemcpyDeviceToHost, s));
+      CUDA_CALL(cudaMemcpyAsync(h_csrColInd_, d_csrColInd_, nv*sizeof(Index), cudaMemcpyDeviceToHost, s));
+      CUDA_CALL(cudaMemcpyAsync(h_csrVal_, d_csrVal_, nv*sizeof(T), cudaMemcpyDeviceToHost, s));
     }
     if (format_ == GrB_SPARSE_MATRIX_CSRCSC && d_cscVal_ && d_cscColPtr_ &&
         d_cscRowInd_ && h_cscVal_ && h_cscColPtr_ && h_cscRowInd_) {
       if (nv > 0)
-        CUDA_CALL(cudaMemcpyAsync(h_cscVal_, d_cscVal_, nv*sizeof(T),
-            cudaMemcpyDeviceToHost, s));
+        CUDA_CALL(cudaMemcpyAsync(h_cscVal_, d_cscVal_, nv*sizeof(T), cudaMemcpyDeviceToHost, s));
       if (!symmetric_ || fresh_host) {
-        CUDA_CALL(cudaMemcpyAsync(h_cscColPtr_, d_cscColPtr_,
-            (ncols_+1)*sizeof(Index), cudaMemcpyDeviceToHost, s));
+        CUDA_CALL(cudaMemcpyAsync(h_cscColPtr_, d_cscColPtr_, (ncols_+1)*sizeof(Index), cudaMemcpyDeviceToHost, s));
         if (nv > 0)
-          CUDA_CALL(cudaMemcpyAsync(h_cscRowInd_, d_cscRowInd_,
-              nv*sizeof(Index), cudaMemcpyDeviceToHost, s));
+          CUDA_CALL(cudaMemcpyAsync(h_cscRowInd_, d_cscRowInd_, nv*sizeof(Index), cudaMemcpyDeviceToHost, s));
       }
     }
     runtime().sync();
@@ -837,8 +801,8 @@ Info SparseMatrix<T>::syncCpu() {
   CHECK(allocateCpu());
   if (h_csrRowPtr_ && h_csrColInd_ && h_csrVal_ &&
       h_cscColPtr_ && h_cscRowInd_ && h_cscVal_)
-    csr2csc(h_cscColPtr_, h_cscRowInd_, h_cscVal_,
-            h_csrRowPtr_, h_csrColInd_, h_csrVal_, nrows_, ncols_);
+    csr2csc(h_cscColPtr_, h_cscRowInd_, h_cscVal_, h_csrRowPtr_, h_csrColInd_,
+        h_csrVal_, nrows_, ncols_);
   else
     return GrB_INVALID_OBJECT;
   return GrB_SUCCESS;

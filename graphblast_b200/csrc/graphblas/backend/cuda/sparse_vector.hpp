@@ -40,22 +40,13 @@ class SparseVector {
   inline Info size(Index* nsize_t) const;
   inline Info nvals(Index* nvals_t) const;
   template <typename BinaryOpT>
-  Info build(const std::vector<Index>* indices,
-             const std::vector<T>*     values,
-             Index                     nvals,
-             BinaryOpT                 dup);
-  Info build(const std::vector<T>* values,
-             Index                 nvals);
-  Info build(Index* indices,
-             T*     values,
-             Index  nvals);
-  Info setElement(T val,
-                  Index index);
-  Info extractElement(T*    val,
-                      Index index);
-  Info extractTuples(std::vector<Index>* indices,
-                     std::vector<T>*     values,
-                     Index*              n);
+  Info build(const std::vector<Index>* indices, const std::vector<T>* values,
+      Index nvals, BinaryOpT dup);
+  Info build(const std::vector<T>* values, Index nvals);
+  Info build(Index* indices, T* values, Index nvals);
+  Info setElement(T val, Index index);
+  Info extractElement(T* val, Index index);
+  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n);
 
   // Handy methods
   const T& operator[](Index ind);
@@ -146,9 +137,7 @@ inline Info SparseVector<T>::nvals(Index* nvals_t) const {
 template <typename T>
 template <typename BinaryOpT>
 Info SparseVector<T>::build(const std::vector<Index>* indices,
-                            const std::vector<T>*     values,
-                            Index                     nvals,
-                            BinaryOpT                 dup) {
+    const std::vector<T>* values, Index nvals, BinaryOpT dup) {
   if (nvals > nsize_) {
     std::cout << "SpVec Build with indices greater than nsize_\n";
     std::cout << "Error: Feature not implemented yet!\n";
@@ -166,8 +155,7 @@ Info SparseVector<T>::build(const std::vector<Index>* indices,
 }
 
 template <typename T>
-Info SparseVector<T>::build(const std::vector<T>* values,
-                            Index                 nvals) {
+Info SparseVector<T>::build(const std::vector<T>* values, Index nvals) {
   std::cout << "Sparse Build with dense input\n";
   std::cout << "Error: Feature not implemented yet!\n";
   return GrB_SUCCESS;
@@ -175,9 +163,7 @@ Info SparseVector<T>::build(const std::vector<T>* values,
 
 // Adopts device pointers; ownership stays with the caller.
 template <typename T>
-Info SparseVector<T>::build(Index* indices,
-                            T*     values,
-                            Index  nvals) {
+Info SparseVector<T>::build(Index* indices, T* values, Index nvals) {
   if (owns_device_) {
     if (d_ind_ != NULL) gbFree(d_ind_);
     if (d_val_ != NULL) gbFree(d_val_);
@@ -207,9 +193,8 @@ Info SparseVector<T>::extractElement(T* val, Index index) {
 }
 
 template <typename T>
-Info SparseVector<T>::extractTuples(std::vector<Index>* indices,
-                                    std::vector<T>*     values,
-                                    Index*              n) {
+Info SparseVector<T>::extractTuples(std::vector<Index>* indices, std::vector<T>* values,
+    Index* n) {
   indices->clear();
   values->clear();
   if (*n > nvals_) {
@@ -253,11 +238,9 @@ Info SparseVector<T>::resize(Index nsize) {
   if (h_ind_old != NULL) memcpy(h_ind_, h_ind_old, to_copy*sizeof(Index));
   if (h_val_old != NULL) memcpy(h_val_, h_val_old, to_copy*sizeof(T));
   if (d_ind_old != NULL)
-    CUDA_CALL(cudaMemcpyAsync(d_ind_, d_ind_old, to_copy*sizeof(Index),
-        cudaMemcpyDeviceToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_ind_, d_ind_old, to_copy*sizeof(Index), cudaMemcpyDeviceToDevice, gbStream()));
   if (d_val_old != NULL)
-    CUDA_CALL(cudaMemcpyAsync(d_val_, d_val_old, to_copy*sizeof(T),
-        cudaMemcpyDeviceToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_val_, d_val_old, to_copy*sizeof(T), cudaMemcpyDeviceToDevice, gbStream()));
   nvals_ = to_copy;
   if (h_ind_old != NULL) free(h_ind_old);
   if (h_val_old != NULL) free(h_val_old);
@@ -342,10 +325,8 @@ template <typename T>
 Info SparseVector<T>::cpuToGpu() {
   CHECK(allocate());
   if (nvals_ > 0) {
-    CUDA_CALL(cudaMemcpyAsync(d_ind_, h_ind_, nvals_*sizeof(Index),
-        cudaMemcpyHostToDevice, gbStream()));
-    CUDA_CALL(cudaMemcpyAsync(d_val_, h_val_, nvals_*sizeof(T),
-        cudaMemcpyHostToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_ind_, h_ind_, nvals_*sizeof(Index), cudaMemcpyHostToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_val_, h_val_, nvals_*sizeof(T), cudaMemcpyHostToDevice, gbStream()));
     runtime().sync();
   }
   need_update_ = false;
@@ -357,10 +338,8 @@ Info SparseVector<T>::gpuToCpu(bool force_update) {
   bool fresh_host = (h_ind_ == NULL);
   CHECK(allocate());
   if ((need_update_ || force_update || fresh_host) && nvals_ > 0) {
-    CUDA_CALL(cudaMemcpyAsync(h_ind_, d_ind_, nvals_*sizeof(Index),
-        cudaMemcpyDeviceToHost, gbStream()));
-    CUDA_CALL(cudaMemcpyAsync(h_val_, d_val_, nvals_*sizeof(T),
-        cudaMemcpyDeviceToHost, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(h_ind_, d_ind_, nvals_*sizeof(Index), cudaMemcpyDeviceToHost, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(h_val_, d_val_, nvals_*sizeof(T), cudaMemcpyDeviceToHost, gbStream()));
     runtime().sync();
   }
   need_update_ = false;

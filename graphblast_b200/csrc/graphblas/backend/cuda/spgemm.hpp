@@ -17,13 +17,9 @@ namespace backend {
 
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
-Info spgemmMasked(SparseMatrix<c>*       C,
-                  const Matrix<m>*       mask,
-                  BinaryOpT              accum,
-                  SemiringT              op,
-                  const SparseMatrix<a>* A,
-                  const SparseMatrix<b>* B,
-                  Descriptor*            desc) {
+Info spgemmMasked(SparseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum,
+    SemiringT op, const SparseMatrix<a>* A, const SparseMatrix<b>* B,
+    Descriptor* desc) {
   Desc_value scmp_mode, inp0_mode, inp1_mode;
   CHECK(desc->get(GrB_MASK, &scmp_mode));
   CHECK(desc->get(GrB_INP0, &inp0_mode));

@@ -37,14 +37,13 @@ namespace backend {
 // pattern or the size changes; steady-state calls skip it.
 template <typename W>
 Info preparePushArenas(Descriptor* desc, Index n, W identity, bool need_acc,
-                       unsigned int** bits_out, W** acc_out) {
+    unsigned int** bits_out, W** acc_out) {
   cudaStream_t s = gbStream();
   const size_t nwords = (static_cast<size_t>(n) + 31)/32;
   unsigned int* bits = reinterpret_cast<unsigned int*>(
       desc->scratch(GB_SCRATCH_BITS, nwords*sizeof(unsigned int)));
   if (!desc->bits_valid_ || desc->bits_words_ < nwords) {
-    CUDA_CALL(cudaMemsetAsync(bits, 0,
-        desc->slot_size_[GB_SCRATCH_BITS], s));
+    CUDA_CALL(cudaMemsetAsync(bits, 0, desc->slot_size_[GB_SCRATCH_BITS], s));
     desc->bits_valid_ = true;
     desc->bits_words_ = desc->slot_size_[GB_SCRATCH_BITS]/sizeof(unsigned int);
   }
@@ -74,14 +73,9 @@ Info preparePushArenas(Descriptor* desc, Index n, W identity, bool need_acc,
 
 template <typename W, typename a, typename U, typename M,
           typename BinaryOpT, typename SemiringT>
-Info spmspvMerge(SparseVector<W>*       w,
-                 const Vector<M>*       mask,
-                 BinaryOpT              accum,
-                 SemiringT              op,
-                 const SparseMatrix<a>* A,
-                 const SparseVector<U>* u,
-                 Descriptor*            desc,
-                 bool*                  prefer_pull = NULL) {
+Info spmspvMerge(SparseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
+    SemiringT op, const SparseMatrix<a>* A, const SparseVector<U>* u, Descriptor* desc,
+    bool* prefer_pull = NULL) {
   // prefer_pull != NULL: the caller can still take the pull direction.  If the
   // frontier's edges are more than GB200_EDGE_SWITCH_PCT percent of all stored entries the
   // push is abandoned before it starts (*prefer_pull = true, w untouched): the
@@ -159,11 +153,9 @@ Info spmspvMerge(SparseVector<W>*       w,
         u->d_ind_, nf);
     GB_KERNEL_CHECK();
     size_t cub_bytes = 0;
-    CUDA_CALL(cub::DeviceScan::ExclusiveSum(NULL, cub_bytes, deg, offs, nf + 1,
-        s));
+    CUDA_CALL(cub::DeviceScan::ExclusiveSum(NULL, cub_bytes, deg, offs, nf + 1, s));
     void* cub_tmp = desc->scratch(GB_SCRATCH_CUB, cub_bytes);
-    CUDA_CALL(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, deg, offs,
-        nf + 1, s));
+    CUDA_CALL(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, deg, offs, nf + 1, s));
   }
 
   // 1b) edge-based direction check (only for frontiers big enough to matter, so
@@ -197,8 +189,7 @@ Info spmspvMerge(SparseVector<W>*       w,
   // 2) expand + combine into the accumulator / bitmap.
   unsigned int* bits;
   W*            acc;
-  CHECK(preparePushArenas<W>(desc, out_size, op.identity(), !struconly, &bits,
-      &acc));
+  CHECK(preparePushArenas<W>(desc, out_size, op.identity(), !struconly, &bits, &acc));
 
   const int grid = runtime().sm_count*8;
   const int mask_mode = use_mask ? (keep_zero ? 2 : 1) : 0;

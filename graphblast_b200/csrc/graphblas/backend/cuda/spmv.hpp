@@ -23,16 +23,9 @@ namespace backend {
 // Generic SpMV into `out` (raw result, no mask/accum).  2 launches (+1 the first
 // time a matrix is used, to compute its tile partition).
 template <typename W, typename a, typename U, typename SemiringT>
-Info spmvMergeLaunch(W*           out,
-                     const Index* tile_rows,
-                     SemiringT    op,
-                     const Index* rowptr,
-                     const Index* colind,
-                     const a*     val,
-                     const U*     u,
-                     Index        nrows,
-                     Index        nnz,
-                     Descriptor*  desc) {
+Info spmvMergeLaunch(W* out, const Index* tile_rows, SemiringT op, const Index* rowptr,
+    const Index* colind, const a* val, const U* u, Index nrows, Index nnz,
+    Descriptor* desc) {
   if (nrows <= 0) return GrB_SUCCESS;
   const long long total = static_cast<long long>(nrows) + nnz;
   const int nctas = static_cast<int>((total + GB_SPMV_TILE - 1)/GB_SPMV_TILE);
@@ -52,11 +45,9 @@ Info spmvMergeLaunch(W*           out,
   typedef decltype(extractAdd(op)) AddT;
   static bool configured = false;      // once per instantiation
   if (!configured) {
-    cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, true,
-        false, W, a, U, MulT, AddT>,
+    cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, true, false, W, a, U, MulT, AddT>,
         cudaFuncAttributePreferredSharedMemoryCarveout, GB_SPMV_CARVEOUT);
-    cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true,
-        true, W, a, U, MulT, AddT>,
+    cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true, true, W, a, U, MulT, AddT>,
         cudaFuncAttributePreferredSharedMemoryCarveout, GB_SPMV_CARVEOUT);
     configured = true;
   }
@@ -85,13 +76,8 @@ Info spmvMergeLaunch(W*           out,
 
 template <typename W, typename a, typename U, typename M,
           typename BinaryOpT,      typename SemiringT>
-Info spmv(DenseVector<W>*        w,
-          const Vector<M>*       mask,
-          BinaryOpT              accum,
-          SemiringT              op,
-          const SparseMatrix<a>* A,
-          const DenseVector<U>*  u,
-          Descriptor*            desc) {
+Info spmv(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
+    const SparseMatrix<a>* A, const DenseVector<U>* u, Descriptor* desc) {
   // Get descriptor parameters for SCMP, REPL, TRAN
   Desc_value scmp_mode, repl_mode, inp0_mode, inp1_mode;
   CHECK(desc->get(GrB_MASK, &scmp_mode));
@@ -323,19 +309,18 @@ Info spmv(DenseVector<W>*        w,
               static_cast<size_t>(ncols_t)*sizeof(Index)));
           Index* rank  = reinterpret_cast<Index*>(gbMalloc(
               static_cast<size_t>(ncols_t)*sizeof(Index)));
-          CUDA_CALL(cudaMemsetAsync(cnt, 0,
-              static_cast<size_t>(ncols_t)*sizeof(int), s));
+          CUDA_CALL(cudaMemsetAsync(cnt, 0, static_cast<size_t>(ncols_t)*sizeof(int), s));
           columnCountKernel<<<gridFor(A->nvals_, 256, 8), 256, 0, s>>>(cnt,
               A_csrColInd, A->nvals_);
           GB_KERNEL_CHECK();
           iotaKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(ids, ncols_t);
           GB_KERNEL_CHECK();
           size_t tmp_bytes = 0;
-          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(NULL, tmp_bytes, cnt,
-              cnt_s, ids, A_t->d_relabel_perm_[which], ncols_t, 0, 32, s));
+          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(NULL, tmp_bytes, cnt, cnt_s, ids, A_t->d_relabel_perm_[which],
+              ncols_t, 0, 32, s));
           void* tmp = gbMalloc(tmp_bytes);
-          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, cnt,
-              cnt_s, ids, A_t->d_relabel_perm_[which], ncols_t, 0, 32, s));
+          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, cnt, cnt_s, ids, A_t->d_relabel_perm_[which],
+              ncols_t, 0, 32, s));
           invertPermKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(rank,
               A_t->d_relabel_perm_[which], ncols_t);
           GB_KERNEL_CHECK();
@@ -355,8 +340,8 @@ Info spmv(DenseVector<W>*        w,
         gather_u  = u_perm;
       }
     }
-    CHECK(spmvMergeLaunch(w_val, A_t->d_spmv_tiles_[which], op, A_csrRowPtr,
-        gather_ci, A_csrVal, gather_u, A_nrows, A->nvals_, desc));
+    CHECK(spmvMergeLaunch(w_val, A_t->d_spmv_tiles_[which], op, A_csrRowPtr, gather_ci,
+        A_csrVal, gather_u, A_nrows, A->nvals_, desc));
 
     if (use_mask) {
       Storage mask_vec_type;

@@ -12,41 +12,44 @@
 namespace graphblas {
 namespace backend {
 
+// In-place on A's host CSR (C is the same object in the only caller, reference
+// example/gtc.cu:80-82): entries above the diagonal are squeezed out row by row,
+// then the CSC is rebuilt from the CSR and both are uploaded again.
 template <typename a, typename c>
-Info trilSparse(SparseMatrix<c>* C,
-                SparseMatrix<a>* A,
-                Descriptor*      desc) {
-  Desc_value backend;
-  CHECK(desc->get(GrB_BACKEND, &backend));
+Info trilSparse(SparseMatrix<c>* C, SparseMatrix<a>* A, Descriptor* desc) {
+  Desc_value where;
+  CHECK(desc->get(GrB_BACKEND, &where));
+  if (desc->debug()) std::cout << "Executing trilSparse\n";
 
-  if (desc->debug())
-    std::cout << "Executing trilSparse\n";
-
-  if (backend == GrB_SEQUENTIAL) {
-    CHECK(A->gpuToCpu());
-    Index kept = 0;
-    Index read = 0;
-    for (Index row = 0; row < A->nrows_; ++row) {
-      const Index row_end = A->h_csrRowPtr_[row+1];
-      A->h_csrRowPtr_[row] = kept;
-      for (; read < row_end; ++read) {
-        const Index col = A->h_csrColInd_[read];
-        if (col <= row) {
-          A->h_csrColInd_[kept] = col;
-          A->h_csrVal_[kept]    = A->h_csrVal_[read];
-          ++kept;
-        }
-      }
-    }
-    A->h_csrRowPtr_[A->nrows_] = kept;
-    A->nvals_ = kept;
-
-    CHECK(C->syncCpu());
-    CHECK(C->cpuToGpu());
-  } else {
+  if (where != GrB_SEQUENTIAL) {
     std::cout << "trilSparse GPU\n";
     std::cout << "Error: Feature not implemented yet!\n";
+    return GrB_SUCCESS;
   }
+
+  CHECK(A->gpuToCpu());
+  Index* const rowptr = A->h_csrRowPtr_;
+  Index* const colind = A->h_csrColInd_;
+  a* const     values = A->h_csrVal_;
+  Index out = 0;                       // next free slot of the squeezed arrays
+  Index in  = 0;                       // next entry to look at
+  for (Index r = 0; r < A->nrows_; ++r) {
+    const Index stop = rowptr[r + 1];  // read before rowptr[r + 1] is overwritten
+    rowptr[r] = out;
+    while (in < stop) {
+      if (colind[in] <= r) {
+        colind[out] = colind[in];
+        values[out] = values[in];
+        ++out;
+      }
+      ++in;
+    }
+  }
+  rowptr[A->nrows_] = out;
+  A->nvals_ = out;
+
+  CHECK(C->syncCpu());
+  CHECK(C->cpuToGpu());
   return GrB_SUCCESS;
 }
 }  // namespace backend

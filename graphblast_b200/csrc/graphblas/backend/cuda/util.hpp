@@ -99,13 +99,11 @@ struct Profiler {
   void reset(cudaStream_t s) {
     ensureCells();
     for (int k = 0; k < GB_PROF_NKINDS; ++k) { used[k] = 0; host_bytes[k] = 0; }
-    CUDA_CALL(cudaMemsetAsync(d_cells, 0,
-        GB_PROF_NKINDS*sizeof(unsigned long long), s));
+    CUDA_CALL(cudaMemsetAsync(d_cells, 0, GB_PROF_NKINDS*sizeof(unsigned long long), s));
   }
 
   // Total milliseconds, launches and bytes of one kind (synchronises).
-  void read(int kind, cudaStream_t s, double* ms, long long* launches,
-            double* bytes) {
+  void read(int kind, cudaStream_t s, double* ms, long long* launches, double* bytes) {
     ensureCells();
     CUDA_CALL(cudaStreamSynchronize(s));
     double total = 0;
@@ -115,8 +113,7 @@ struct Profiler {
       total += t;
     }
     unsigned long long cell = 0;
-    CUDA_CALL(cudaMemcpy(&cell, d_cells + kind, sizeof(cell),
-        cudaMemcpyDeviceToHost));
+    CUDA_CALL(cudaMemcpy(&cell, d_cells + kind, sizeof(cell), cudaMemcpyDeviceToHost));
     *ms = total;
     *launches = static_cast<long long>(used[kind]);
     *bytes = host_bytes[kind] + static_cast<double>(cell);
@@ -158,8 +155,7 @@ struct Runtime {
   template <typename T>
   T fetch(const T* d_ptr) {
     init();
-    CUDA_CALL(cudaMemcpyAsync(h_pinned, d_ptr, sizeof(T),
-        cudaMemcpyDeviceToHost, stream));
+    CUDA_CALL(cudaMemcpyAsync(h_pinned, d_ptr, sizeof(T), cudaMemcpyDeviceToHost, stream));
     CUDA_CALL(cudaStreamSynchronize(stream));
     return *reinterpret_cast<T*>(h_pinned);
   }
@@ -167,8 +163,7 @@ struct Runtime {
   template <typename T>
   void fetch2(const T* d_ptr, T* a, T* b) {
     init();
-    CUDA_CALL(cudaMemcpyAsync(h_pinned, d_ptr, 2*sizeof(T),
-        cudaMemcpyDeviceToHost, stream));
+    CUDA_CALL(cudaMemcpyAsync(h_pinned, d_ptr, 2*sizeof(T), cudaMemcpyDeviceToHost, stream));
     CUDA_CALL(cudaStreamSynchronize(stream));
     *a = reinterpret_cast<T*>(h_pinned)[0];
     *b = reinterpret_cast<T*>(h_pinned)[1];
@@ -189,11 +184,9 @@ struct Runtime {
 
   void mailInit() {
     if (h_mail != NULL) return;
-    CUDA_CALL(cudaHostAlloc(reinterpret_cast<void**>(&h_mail),
-        8*sizeof(unsigned long long), cudaHostAllocMapped));
+    CUDA_CALL(cudaHostAlloc(reinterpret_cast<void**>(&h_mail), 8*sizeof(unsigned long long), cudaHostAllocMapped));
     for (int i = 0; i < 8; ++i) h_mail[i] = 0ull;
-    CUDA_CALL(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_mail),
-        h_mail, 0));
+    CUDA_CALL(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_mail), h_mail, 0));
     mail_seq = 0;
   }
   // Ticket for the next post (24 bits, never 0) and where the kernel writes it.
@@ -202,7 +195,7 @@ struct Runtime {
   // Value posted under `ticket`; falls back to a stream-ordered read of
   // d_fallback if the slot was reused by a later post or nothing arrives.
   unsigned long long mailWait(int slot, unsigned long long ticket,
-                              const unsigned long long* d_fallback) {
+      const unsigned long long* d_fallback) {
     volatile unsigned long long* p = h_mail + slot;
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned long long spin = 0;; ++spin) {
@@ -238,8 +231,7 @@ inline void* gbMalloc(size_t bytes) {
     cudaMemPool_t pool;
     CUDA_CALL(cudaDeviceGetDefaultMemPool(&pool, rt.device));
     unsigned long long threshold = ~0ull;
-    CUDA_CALL(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold,
-        &threshold));
+    CUDA_CALL(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     pool_ready = true;
   }
   void* p = NULL;
@@ -271,23 +263,21 @@ inline void printMemory(const char* str) {
 }
 
 template <typename T>
-void printDevice(const char* str, const T* array, int length = 40,
-                 bool limit = true) {
+void printDevice(const char* str, const T* array, int length = 40, bool limit = true) {
   if (limit && length > 40) length = 40;
   if (length <= 0 || array == NULL) {
     std::cout << str << ": (empty)\n";
     return;
   }
   T* temp = reinterpret_cast<T*>(malloc(length*sizeof(T)));
-  CUDA_CALL(cudaMemcpyAsync(temp, array, length*sizeof(T),
-      cudaMemcpyDeviceToHost, gbStream()));
+  CUDA_CALL(cudaMemcpyAsync(temp, array, length*sizeof(T), cudaMemcpyDeviceToHost, gbStream()));
   runtime().sync();
   printArray(str, temp, length, limit);
   if (temp) free(temp);
 }
 
-inline void printState(bool use_mask, bool use_accum, bool use_scmp,
-                       bool use_repl, bool use_tran) {
+inline void printState(bool use_mask, bool use_accum, bool use_scmp, bool use_repl,
+    bool use_tran) {
   std::cout << "Mask: " << use_mask  << std::endl;
   std::cout << "Accum:" << use_accum << std::endl;
   std::cout << "SCMP: " << use_scmp  << std::endl;

@@ -43,22 +43,14 @@ class Vector {
   Info size(Index* nsize_t);
   Info nvals(Index* nvals_t);
   template <typename BinaryOpT>
-  Info build(const std::vector<Index>* indices,
-             const std::vector<T>*     values,
-             Index                     nvals,
-             BinaryOpT                 dup);
-  Info build(const std::vector<T>* values,
-             Index                 nvals);
-  Info build(Index* indices,
-             T*     values,
-             Index nvals);
-  Info build(T*    values,
-             Index nvals);
+  Info build(const std::vector<Index>* indices, const std::vector<T>* values,
+      Index nvals, BinaryOpT dup);
+  Info build(const std::vector<T>* values, Index nvals);
+  Info build(Index* indices, T* values, Index nvals);
+  Info build(T* values, Index nvals);
   Info setElement(T val, Index index);
   Info extractElement(T* val, Index index);
-  Info extractTuples(std::vector<Index>* indices,
-                     std::vector<T>*     values,
-                     Index*              n);
+  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n);
   Info extractTuples(std::vector<T>* values, Index* n);
 
   // handy methods
@@ -147,32 +139,26 @@ Info Vector<T>::nvals(Index* nvals_t) {
 
 template <typename T>
 template <typename BinaryOpT>
-Info Vector<T>::build(const std::vector<Index>* indices,
-                      const std::vector<T>*     values,
-                      Index                     nvals,
-                      BinaryOpT                 dup) {
+Info Vector<T>::build(const std::vector<Index>* indices, const std::vector<T>* values,
+    Index nvals, BinaryOpT dup) {
   vec_type_ = GrB_SPARSE;
   return sparse_.build(indices, values, nvals, dup);
 }
 
 template <typename T>
-Info Vector<T>::build(const std::vector<T>* values,
-                      Index                 nvals) {
+Info Vector<T>::build(const std::vector<T>* values, Index nvals) {
   vec_type_ = GrB_DENSE;
   return dense_.build(values, nvals);
 }
 
 template <typename T>
-Info Vector<T>::build(Index* indices,
-                      T*     values,
-                      Index nvals) {
+Info Vector<T>::build(Index* indices, T* values, Index nvals) {
   vec_type_ = GrB_SPARSE;
   return sparse_.build(indices, values, nvals);
 }
 
 template <typename T>
-Info Vector<T>::build(T*    values,
-                      Index nvals) {
+Info Vector<T>::build(T* values, Index nvals) {
   vec_type_ = GrB_DENSE;
   return dense_.build(values, nvals);
 }
@@ -192,9 +178,8 @@ Info Vector<T>::extractElement(T* val, Index index) {
 }
 
 template <typename T>
-Info Vector<T>::extractTuples(std::vector<Index>* indices,
-                              std::vector<T>*     values,
-                              Index*              n) {
+Info Vector<T>::extractTuples(std::vector<Index>* indices, std::vector<T>* values,
+    Index* n) {
   if (vec_type_ == GrB_SPARSE)
     return sparse_.extractTuples(indices, values, n);
   else if (vec_type_ == GrB_DENSE)
@@ -204,8 +189,7 @@ Info Vector<T>::extractTuples(std::vector<Index>* indices,
 
 // A sparse vector is densified with fill value 0 first (reference :208-217).
 template <typename T>
-Info Vector<T>::extractTuples(std::vector<T>* values,
-                              Index*          n) {
+Info Vector<T>::extractTuples(std::vector<T>* values, Index* n) {
   if (vec_type_ == GrB_SPARSE) {
     CHECK(sparse2dense(0.f));
     return dense_.extractTuples(values, n);

@@ -17,10 +17,7 @@
 namespace graphblas {
 namespace algorithm {
 
-inline float bfs(Vector<float>*       v,
-                 const Matrix<float>* A,
-                 Index                s,
-                 Descriptor*          desc) {
+inline float bfs(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor* desc) {
   Index n;
   CHECK(A->nrows(&n));
   CHECK(v->fill(0.f));

@@ -24,20 +24,14 @@ inline Info prNormalize(Matrix<float>* A, float alpha, Descriptor* desc) {
   Index n;
   CHECK(A->nrows(&n));
   Vector<float> outdegrees(n);
-  CHECK((reduce<float, float, float>(&outdegrees, GrB_NULL, GrB_NULL,
-      PlusMonoid<float>(), A, desc)));
-  CHECK((eWiseMult<float, float, float, float>(A, GrB_NULL, GrB_NULL,
-      PlusMultipliesSemiring<float>(), A, alpha, desc)));
-  CHECK((eWiseMult<float, float, float, float>(A, GrB_NULL, GrB_NULL,
-      PlusDividesSemiring<float>(), A, &outdegrees, desc)));
+  CHECK((reduce<float, float, float>(&outdegrees, GrB_NULL, GrB_NULL, PlusMonoid<float>(), A, desc)));
+  CHECK((eWiseMult<float, float, float, float>(A, GrB_NULL, GrB_NULL, PlusMultipliesSemiring<float>(), A, alpha, desc)));
+  CHECK((eWiseMult<float, float, float, float>(A, GrB_NULL, GrB_NULL, PlusDividesSemiring<float>(), A, &outdegrees, desc)));
   return GrB_SUCCESS;
 }
 
-inline float pr(Vector<float>*       p,
-                const Matrix<float>* A,
-                float                alpha,
-                float                eps,
-                Descriptor*          desc) {
+inline float pr(Vector<float>* p, const Matrix<float>* A, float alpha, float eps,
+    Descriptor* desc) {
   Index n;
   CHECK(A->nrows(&n));
 

@@ -19,10 +19,7 @@
 namespace graphblas {
 namespace algorithm {
 
-inline float sssp(Vector<float>*       v,
-                  const Matrix<float>* A,
-                  Index                s,
-                  Descriptor*          desc) {
+inline float sssp(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor* desc) {
   const float kInf = std::numeric_limits<float>::max();
   Index n;
   CHECK(A->nrows(&n));

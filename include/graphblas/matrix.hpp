@@ -42,11 +42,8 @@ class Matrix {
   // Host COO triples; empty triples + dat_name means "load the binary cache".
   template <typename BinaryOpT>
   Info build(const std::vector<Index>* row_indices,
-             const std::vector<Index>* col_indices,
-             const std::vector<T>*     values,
-             Index                     nvals,
-             BinaryOpT                 dup,
-             char*                     dat_name = NULL) {
+      const std::vector<Index>* col_indices, const std::vector<T>* values, Index nvals,
+      BinaryOpT dup, char* dat_name = NULL) {
     if (row_indices == NULL || col_indices == NULL || values == NULL)
       return GrB_NULL_POINTER;
     const bool empty = row_indices->empty() && col_indices->empty() &&
@@ -74,10 +71,8 @@ class Matrix {
     if (val == NULL) return GrB_NULL_POINTER;
     return matrix_.extractElement(val, row_index, col_index);
   }
-  Info extractTuples(std::vector<Index>* row_indices,
-                     std::vector<Index>* col_indices,
-                     std::vector<T>*     values,
-                     Index*              n) {
+  Info extractTuples(std::vector<Index>* row_indices, std::vector<Index>* col_indices,
+      std::vector<T>* values, Index* n) {
     if (row_indices == NULL || col_indices == NULL || values == NULL ||
         n == NULL)
       return GrB_NULL_POINTER;

@@ -146,8 +146,7 @@ void setEnv(const char* key, T default_val) {
 // either (std::sort of tuples compared on (row, col) only, :149-195).
 template <typename T>
 void customSort(std::vector<graphblas::Index>* row_indices,
-                std::vector<graphblas::Index>* col_indices,
-                std::vector<T>*                values) {
+    std::vector<graphblas::Index>* col_indices, std::vector<T>* values) {
   const size_t n = row_indices->size();
   std::vector<size_t> perm(n);
   std::iota(perm.begin(), perm.end(), static_cast<size_t>(0));
@@ -172,10 +171,8 @@ void customSort(std::vector<graphblas::Index>* row_indices,
 // Entries with explicit values of type mtxT (int or float in the file).
 template <typename T, typename mtxT>
 void readTuples(std::vector<graphblas::Index>* row_indices,
-                std::vector<graphblas::Index>* col_indices,
-                std::vector<T>*                values,
-                graphblas::Index               nvals,
-                FILE*                          f) {
+    std::vector<graphblas::Index>* col_indices, std::vector<T>* values,
+    graphblas::Index nvals, FILE* f) {
   const char* fmt = (typeid(mtxT) == typeid(int)) ? "%d" : "%f";
   for (graphblas::Index i = 0; i < nvals; i++) {
     graphblas::Index row_ind, col_ind;
@@ -195,10 +192,8 @@ void readTuples(std::vector<graphblas::Index>* row_indices,
 // Pattern entries: value 1.
 template <typename T>
 void readTuples(std::vector<graphblas::Index>* row_indices,
-                std::vector<graphblas::Index>* col_indices,
-                std::vector<T>*                values,
-                graphblas::Index               nvals,
-                FILE*                          f) {
+    std::vector<graphblas::Index>* col_indices, std::vector<T>* values,
+    graphblas::Index nvals, FILE* f) {
   for (graphblas::Index i = 0; i < nvals; i++) {
     graphblas::Index row_ind, col_ind;
     if (fscanf(f, "%d", &row_ind) == EOF) {
@@ -215,10 +210,8 @@ void readTuples(std::vector<graphblas::Index>* row_indices,
 // Symmetrise (optional), sort, drop self-loops and duplicates.
 template <typename T>
 void removeSelfloop(std::vector<graphblas::Index>* row_indices,
-                    std::vector<graphblas::Index>* col_indices,
-                    std::vector<T>*                values,
-                    graphblas::Index*              nvals,
-                    bool                           undirected) {
+    std::vector<graphblas::Index>* col_indices, std::vector<T>* values,
+    graphblas::Index* nvals, bool undirected) {
   bool remove_self_loops = getEnv("GRB_UTIL_REMOVE_SELFLOOP", true);
 
   if (undirected) {
@@ -282,16 +275,10 @@ inline char* convert(const char* fname, bool is_undirected = true) {
 }
 
 template <typename T>
-int readMtx(const char*                    fname,
-            std::vector<graphblas::Index>* row_indices,
-            std::vector<graphblas::Index>* col_indices,
-            std::vector<T>*                values,
-            graphblas::Index*              nrows,
-            graphblas::Index*              ncols,
-            graphblas::Index*              nvals,
-            int                            directed,
-            bool                           mtxinfo,
-            char**                         dat_name = NULL) {
+int readMtx(const char* fname, std::vector<graphblas::Index>* row_indices,
+    std::vector<graphblas::Index>* col_indices, std::vector<T>* values,
+    graphblas::Index* nrows, graphblas::Index* ncols, graphblas::Index* nvals,
+    int directed, bool mtxinfo, char** dat_name = NULL) {
   int ret_code;
   MM_typecode matcode;
   FILE* f;
@@ -346,8 +333,7 @@ int readMtx(const char*                    fname,
 }
 
 template <typename T>
-void printArray(const char* str, const T* array, int length = 40,
-                bool limit = true) {
+void printArray(const char* str, const T* array, int length = 40, bool limit = true) {
   if (limit && length > 40) length = 40;
   std::cout << str << ":\n";
   for (int i = 0; i < length; i++)
@@ -357,7 +343,7 @@ void printArray(const char* str, const T* array, int length = 40,
 
 template <typename T>
 void printArray(const char* str, const std::vector<T>& array, int length = 40,
-                bool limit = true) {
+    bool limit = true) {
   if (limit && length > 40) length = 40;
   std::cout << str << ":\n";
   for (int i = 0; i < length; i++)
@@ -386,14 +372,9 @@ using namespace graphblas;
 // kept, so a (row, col)-sorted input yields sorted rows (reference :502-556
 // sorts a copy first; the result is the same CSR).
 template <typename T>
-void coo2csr(Index*                    csrRowPtr,
-             Index*                    csrColInd,
-             T*                        csrVal,
-             const std::vector<Index>& row_indices,
-             const std::vector<Index>& col_indices,
-             const std::vector<T>&     values,
-             Index                     nrows,
-             Index                     ncols) {
+void coo2csr(Index* csrRowPtr, Index* csrColInd, T* csrVal,
+    const std::vector<Index>& row_indices, const std::vector<Index>& col_indices,
+    const std::vector<T>& values, Index nrows, Index ncols) {
   const Index nvals = row_indices.size();
   std::vector<Index> r = row_indices;
   std::vector<Index> c = col_indices;
@@ -414,27 +395,16 @@ void coo2csr(Index*                    csrRowPtr,
 }
 
 template <typename T>
-void coo2csc(Index*                    cscColPtr,
-             Index*                    cscRowInd,
-             T*                        cscVal,
-             const std::vector<Index>& row_indices,
-             const std::vector<Index>& col_indices,
-             const std::vector<T>&     values,
-             Index                     nrows,
-             Index                     ncols) {
-  return coo2csr(cscColPtr, cscRowInd, cscVal, col_indices, row_indices, values,
-      ncols, nrows);
+void coo2csc(Index* cscColPtr, Index* cscRowInd, T* cscVal,
+    const std::vector<Index>& row_indices, const std::vector<Index>& col_indices,
+    const std::vector<T>& values, Index nrows, Index ncols) {
+  return coo2csr(cscColPtr, cscRowInd, cscVal, col_indices, row_indices, values, ncols,
+      nrows);
 }
 
 template <typename T>
-void csr2csc(Index*       cscColPtr,
-             Index*       cscRowInd,
-             T*           cscVal,
-             const Index* csrRowPtr,
-             const Index* csrColInd,
-             const T*     csrVal,
-             Index        nrows,
-             Index        ncols) {
+void csr2csc(Index* cscColPtr, Index* cscRowInd, T* cscVal, const Index* csrRowPtr,
+    const Index* csrColInd, const T* csrVal, Index nrows, Index ncols) {
   const Index nvals = csrRowPtr[nrows];
   std::vector<Index> row_indices(nvals, 0);
   std::vector<Index> col_indices(nvals, 0);
@@ -446,8 +416,8 @@ void csr2csc(Index*       cscColPtr,
       values[k]      = csrVal[k];
     }
   }
-  return coo2csc(cscColPtr, cscRowInd, cscVal, row_indices, col_indices, values,
-      ncols, nrows);
+  return coo2csc(cscColPtr, cscRowInd, cscVal, row_indices, col_indices, values, ncols,
+      nrows);
 }
 
 #endif  // GRAPHBLAS_UTIL_HPP_

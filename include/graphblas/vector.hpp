@@ -30,7 +30,7 @@ class Vector {
   }
   template <typename BinaryOpT>
   Info build(const std::vector<Index>* indices, const std::vector<T>* values,
-             Index nvals, BinaryOpT dup) {
+      Index nvals, BinaryOpT dup) {
     if (indices == NULL || values == NULL) return GrB_NULL_POINTER;
     return vector_.build(indices, values, nvals, dup);
   }
@@ -54,8 +54,7 @@ class Vector {
     if (val == NULL) return GrB_NULL_POINTER;
     return vector_.extractElement(val, index);
   }
-  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values,
-                     Index* n) {
+  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n) {
     if (indices == NULL || values == NULL || n == NULL) return GrB_NULL_POINTER;
     return vector_.extractTuples(indices, values, n);
   }
