@@ -86,6 +86,175 @@ class Vector {
   }
 };
 
+// ---- storage state and conversions (the direction switch lives here) ----
+
+template <typename T>
+Info Vector<T>::convert(T identity, float switchpoint, Descriptor* desc) {
+  Index nvals_t;
+  Index nsize_t;
+  if (vec_type_ == GrB_SPARSE) {
+    CHECK(sparse_.nvals(&nvals_t));
+    CHECK(sparse_.size(&nsize_t));
+  } else if (vec_type_ == GrB_DENSE) {
+    CHECK(dense_.computeNnz(&nvals_t, identity, desc));
+    CHECK(dense_.nvals(&nsize_t));
+  } else {
+    return GrB_UNINITIALIZED_OBJECT;
+  }
+
+  float ratio = static_cast<float>(nvals_t)/nsize_t;
+  if (desc->dirinfo())
+    std::cout << "Nnz ratio: " << ratio << " Switch point: "
+        << switchpoint << std::endl;
+
+  if (vec_type_ == GrB_SPARSE) {
+    if (ratio > switchpoint && ratio > ratio_)
+      CHECK(sparse2dense(identity, desc));
+    else
+      ratio_ = ratio;
+  } else if (vec_type_ == GrB_DENSE) {
+    if (ratio <= switchpoint && ratio < ratio_)
+      CHECK(dense2sparse(identity, desc));
+    else
+      ratio_ = ratio;
+  }
+  return GrB_SUCCESS;
+}
+
+// With --opreuse the dense array is left untouched: the fused Boolean pull reads
+// the mask instead of the frontier (reference vector.hpp:344-357).
+template <typename T>
+Info Vector<T>::sparse2dense(T identity, Descriptor* desc) {
+  if (vec_type_ == GrB_DENSE) return GrB_SUCCESS;
+  if (vec_type_ == GrB_UNKNOWN) {
+    CHECK(setStorage(GrB_DENSE));
+    return GrB_SUCCESS;
+  }
+
+  if (desc != NULL && desc->dirinfo())
+    std::cout << "Converting from sparse to dense!\n";
+
+  CHECK(setStorage(GrB_DENSE));
+  const Index nvals = sparse_.nvals_;
+
+  bool keep_bits = false;
+  if (desc == NULL || !desc->opreuse()) {
+    CHECK(dense_.fill(identity));
+    if (nvals > 0) {
+      const int nt = 256;
+      if (desc != NULL && desc->struconly()) {
+        scatterConstKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
+            dense_.d_val_, sparse_.d_ind_, (T)1, nvals);
+        if (identity == static_cast<T>(0) && dense_.bits_valid_) {
+          GB_KERNEL_CHECK();
+          scatterBitsKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
+              dense_.d_bits_, sparse_.d_ind_, nvals);
+          keep_bits = true;
+        }
+      } else
+        scatterValsKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
+            dense_.d_val_, sparse_.d_ind_, sparse_.d_val_, nvals);
+      GB_KERNEL_CHECK();
+    }
+  }
+
+  vec_type_            = GrB_DENSE;
+  dense_.need_update_  = true;
+  dense_.nnz_          = nvals;
+  dense_.nnz_valid_    = false;
+  dense_.bits_valid_   = keep_bits;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::dense2sparse(T identity, Descriptor* desc) {
+  if (vec_type_ == GrB_SPARSE) return GrB_INVALID_OBJECT;
+
+  if (desc->dirinfo())
+    std::cout << "Converting from dense to sparse!\n";
+
+  CHECK(dense_.allocateGpu());
+  CHECK(sparse_.allocateGpu());
+  const Index n = dense_.nvals_;
+  const Index nitems = (n + 7)/8;
+
+  LoadBalanceMode mxv_mode = getEnv("GRB_LOAD_BALANCE_MODE",
+      GrB_LOAD_BALANCE_MERGE);
+
+  // Lazy values are only tolerable on the structure-only bitmap path below.
+  if (dense_.vals_stale_ &&
+      !(identity == static_cast<T>(0) && desc->struconly() &&
+        mxv_mode == GrB_LOAD_BALANCE_MERGE))
+    CHECK(dense_.materialize());
+
+  Index count;
+  if (dense_.bits_valid_ && identity == static_cast<T>(0)) {
+    // Compact the bitmap shadow: n/32 words instead of n values.
+    const Index nwords = (n + 31)/32;
+    if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
+      DenseBitsCompactSource<T, true> src;
+      src.bits = dense_.d_bits_; src.u = dense_.d_val_;
+      src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+      count = compactOrdered(src, nwords, desc);
+    } else {
+      DenseBitsCompactSource<T, false> src;
+      src.bits = dense_.d_bits_; src.u = dense_.d_val_;
+      src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+      count = compactOrdered(src, nwords, desc);
+    }
+  } else if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
+    DenseCompactSource<T, true> src;
+    src.u = dense_.d_val_; src.identity = identity; src.n = n;
+    src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+    count = compactOrdered(src, nitems, desc);
+  } else {
+    DenseCompactSource<T, false> src;
+    src.u = dense_.d_val_; src.identity = identity; src.n = n;
+    src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
+    count = compactOrdered(src, nitems, desc);
+  }
+  sparse_.nvals_ = count;
+
+  if (desc->debug()) {
+    std::cout << "Dense frontier size: " << n << std::endl;
+    std::cout << "Sparse frontier size: " << sparse_.nvals_ << std::endl;
+  }
+
+  vec_type_ = GrB_SPARSE;
+  sparse_.need_update_ = true;
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+Info Vector<T>::swap(Vector* rhs) {  // NOLINT(build/include_what_you_use)
+  if (vec_type_ != rhs->vec_type_ || vec_type_ == GrB_UNKNOWN)
+    return GrB_INVALID_OBJECT;
+
+  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.swap(&rhs->sparse_));
+  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.swap(&rhs->dense_));
+
+  std::swap(nsize_, rhs->nsize_);
+  std::swap(nvals_, rhs->nvals_);
+  std::swap(ratio_, rhs->ratio_);
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+inline Info Vector<T>::setStorage(Storage vec_type) {
+  vec_type_ = vec_type;
+  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.allocateGpu());
+  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.allocateGpu());
+  return GrB_SUCCESS;
+}
+
+template <typename T>
+inline Info Vector<T>::getStorage(Storage* vec_type) const {
+  *vec_type = vec_type_;
+  return GrB_SUCCESS;
+}
+
+// ---- construction, element access and forwarding to the active storage ----
+
 template <typename T>
 Info Vector<T>::nnew(Index nsize_t) {
   nsize_ = nsize_t;
@@ -238,171 +407,6 @@ Info Vector<T>::print(bool force_update) {
 
 template <typename T>
 Info Vector<T>::countUnique(Index* count) {
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-inline Info Vector<T>::setStorage(Storage vec_type) {
-  vec_type_ = vec_type;
-  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.allocateGpu());
-  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.allocateGpu());
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-inline Info Vector<T>::getStorage(Storage* vec_type) const {
-  *vec_type = vec_type_;
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-Info Vector<T>::convert(T identity, float switchpoint, Descriptor* desc) {
-  Index nvals_t;
-  Index nsize_t;
-  if (vec_type_ == GrB_SPARSE) {
-    CHECK(sparse_.nvals(&nvals_t));
-    CHECK(sparse_.size(&nsize_t));
-  } else if (vec_type_ == GrB_DENSE) {
-    CHECK(dense_.computeNnz(&nvals_t, identity, desc));
-    CHECK(dense_.nvals(&nsize_t));
-  } else {
-    return GrB_UNINITIALIZED_OBJECT;
-  }
-
-  float ratio = static_cast<float>(nvals_t)/nsize_t;
-  if (desc->dirinfo())
-    std::cout << "Nnz ratio: " << ratio << " Switch point: "
-        << switchpoint << std::endl;
-
-  if (vec_type_ == GrB_SPARSE) {
-    if (ratio > switchpoint && ratio > ratio_)
-      CHECK(sparse2dense(identity, desc));
-    else
-      ratio_ = ratio;
-  } else if (vec_type_ == GrB_DENSE) {
-    if (ratio <= switchpoint && ratio < ratio_)
-      CHECK(dense2sparse(identity, desc));
-    else
-      ratio_ = ratio;
-  }
-  return GrB_SUCCESS;
-}
-
-// With --opreuse the dense array is left untouched: the fused Boolean pull reads
-// the mask instead of the frontier (reference vector.hpp:344-357).
-template <typename T>
-Info Vector<T>::sparse2dense(T identity, Descriptor* desc) {
-  if (vec_type_ == GrB_DENSE) return GrB_SUCCESS;
-  if (vec_type_ == GrB_UNKNOWN) {
-    CHECK(setStorage(GrB_DENSE));
-    return GrB_SUCCESS;
-  }
-
-  if (desc != NULL && desc->dirinfo())
-    std::cout << "Converting from sparse to dense!\n";
-
-  CHECK(setStorage(GrB_DENSE));
-  const Index nvals = sparse_.nvals_;
-
-  bool keep_bits = false;
-  if (desc == NULL || !desc->opreuse()) {
-    CHECK(dense_.fill(identity));
-    if (nvals > 0) {
-      const int nt = 256;
-      if (desc != NULL && desc->struconly()) {
-        scatterConstKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
-            dense_.d_val_, sparse_.d_ind_, (T)1, nvals);
-        if (identity == static_cast<T>(0) && dense_.bits_valid_) {
-          GB_KERNEL_CHECK();
-          scatterBitsKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
-              dense_.d_bits_, sparse_.d_ind_, nvals);
-          keep_bits = true;
-        }
-      } else
-        scatterValsKernel<<<gridFor(nvals, nt), nt, 0, gbStream()>>>(
-            dense_.d_val_, sparse_.d_ind_, sparse_.d_val_, nvals);
-      GB_KERNEL_CHECK();
-    }
-  }
-
-  vec_type_            = GrB_DENSE;
-  dense_.need_update_  = true;
-  dense_.nnz_          = nvals;
-  dense_.nnz_valid_    = false;
-  dense_.bits_valid_   = keep_bits;
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-Info Vector<T>::dense2sparse(T identity, Descriptor* desc) {
-  if (vec_type_ == GrB_SPARSE) return GrB_INVALID_OBJECT;
-
-  if (desc->dirinfo())
-    std::cout << "Converting from dense to sparse!\n";
-
-  CHECK(dense_.allocateGpu());
-  CHECK(sparse_.allocateGpu());
-  const Index n = dense_.nvals_;
-  const Index nitems = (n + 7)/8;
-
-  LoadBalanceMode mxv_mode = getEnv("GRB_LOAD_BALANCE_MODE",
-      GrB_LOAD_BALANCE_MERGE);
-
-  // Lazy values are only tolerable on the structure-only bitmap path below.
-  if (dense_.vals_stale_ &&
-      !(identity == static_cast<T>(0) && desc->struconly() &&
-        mxv_mode == GrB_LOAD_BALANCE_MERGE))
-    CHECK(dense_.materialize());
-
-  Index count;
-  if (dense_.bits_valid_ && identity == static_cast<T>(0)) {
-    // Compact the bitmap shadow: n/32 words instead of n values.
-    const Index nwords = (n + 31)/32;
-    if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
-      DenseBitsCompactSource<T, true> src;
-      src.bits = dense_.d_bits_; src.u = dense_.d_val_;
-      src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
-      count = compactOrdered(src, nwords, desc);
-    } else {
-      DenseBitsCompactSource<T, false> src;
-      src.bits = dense_.d_bits_; src.u = dense_.d_val_;
-      src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
-      count = compactOrdered(src, nwords, desc);
-    }
-  } else if (desc->struconly() && mxv_mode == GrB_LOAD_BALANCE_MERGE) {
-    DenseCompactSource<T, true> src;
-    src.u = dense_.d_val_; src.identity = identity; src.n = n;
-    src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
-    count = compactOrdered(src, nitems, desc);
-  } else {
-    DenseCompactSource<T, false> src;
-    src.u = dense_.d_val_; src.identity = identity; src.n = n;
-    src.out_ind = sparse_.d_ind_; src.out_val = sparse_.d_val_;
-    count = compactOrdered(src, nitems, desc);
-  }
-  sparse_.nvals_ = count;
-
-  if (desc->debug()) {
-    std::cout << "Dense frontier size: " << n << std::endl;
-    std::cout << "Sparse frontier size: " << sparse_.nvals_ << std::endl;
-  }
-
-  vec_type_ = GrB_SPARSE;
-  sparse_.need_update_ = true;
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-Info Vector<T>::swap(Vector* rhs) {  // NOLINT(build/include_what_you_use)
-  if (vec_type_ != rhs->vec_type_ || vec_type_ == GrB_UNKNOWN)
-    return GrB_INVALID_OBJECT;
-
-  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.swap(&rhs->sparse_));
-  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.swap(&rhs->dense_));
-
-  std::swap(nsize_, rhs->nsize_);
-  std::swap(nvals_, rhs->nvals_);
-  std::swap(ratio_, rhs->ratio_);
   return GrB_SUCCESS;
 }
 }  // namespace backend
