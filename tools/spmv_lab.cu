@@ -112,7 +112,7 @@ float runMerge(float* w, const int* rowptr, const int* colind, const float* val,
   thrust::device_vector<float> cval(nctas);
   spmvMergePartitionKernel<<<(nctas + 256)/256, 256>>>(
       thrust::raw_pointer_cast(tiles.data()), rowptr, n, nnz, nctas, tile);
-  auto kern = spmvMergeKernelT<NT, IPT, !LaneMajor, Gather, LaneMajor, float, float, float,
+  auto kern = spmvMergeKernelT<NT, IPT, !LaneMajor, (Gather ? 1 : 0), LaneMajor, float, float, float,
       decltype(graphblas::extractMul(op)), decltype(graphblas::extractAdd(op))>;
   if (carveout >= 0)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -125,7 +125,7 @@ float runMerge(float* w, const int* rowptr, const int* colind, const float* val,
     kern<<<nctas, NT>>>(w, thrust::raw_pointer_cast(tiles.data()),
         thrust::raw_pointer_cast(crow.data()),
         thrust::raw_pointer_cast(cval.data()), rowptr, colind, val, u, n, nnz,
-        op.identity(), graphblas::extractMul(op), graphblas::extractAdd(op));
+        op.identity(), graphblas::extractMul(op), graphblas::extractAdd(op), 0);
     spmvCarryFixupKernel<<<(nctas + 255)/256, 256>>>(w,
         thrust::raw_pointer_cast(crow.data()),
         thrust::raw_pointer_cast(cval.data()), nctas, graphblas::extractAdd(op));
