@@ -416,7 +416,10 @@ Info DenseVector<T>::fill(T val) {
   zero_one_ = false;
   vals_stale_ = false;
   // bitmap shadow of a constant vector: all zero or all one
-  CUDA_CALL(cudaMemsetAsync(bitsStorage(), (val != static_cast<T>(0)) ? 0xff : 0, bitWords()*sizeof(unsigned int), gbStream()));
+  // (tail bits past nvals_ stay clear: consumers read whole words)
+  fillBitmapKernel<<<gridFor(bitWords(), 256), 256, 0, gbStream()>>>(
+      bitsStorage(), nvals_, val != static_cast<T>(0));
+  GB_KERNEL_CHECK();
   bits_valid_ = true;
   return GrB_SUCCESS;
 }

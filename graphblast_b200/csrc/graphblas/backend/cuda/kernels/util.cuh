@@ -64,6 +64,21 @@ __global__ void countNonIdentityKernel(unsigned long long* counter,
     atomicAdd(counter, static_cast<unsigned long long>(total));
 }
 
+// Bitmap of a constant vector of n elements: every word all-zero, or all-one with
+// the bits past n in the last word CLEAR (whole-word consumers — popcount,
+// ordered compaction — rely on the tail being zero).
+__global__ void fillBitmapKernel(unsigned int* __restrict__ bits, Index n,
+                                 bool ones) {
+  Index w = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  const Index nwords = (n + 31) >> 5;
+  for (; w < nwords; w += stride) {
+    unsigned int word = ones ? 0xffffffffu : 0u;
+    if (ones && w == nwords - 1 && (n & 31) != 0) word = (1u << (n & 31)) - 1u;
+    bits[w] = word;
+  }
+}
+
 // bits = bitmap of {i : u[i] != 0}; one 32-bit word per warp-iteration.
 template <typename T>
 __global__ void denseToBitmapKernel(unsigned int* __restrict__ bits,

@@ -103,6 +103,11 @@ Info mxvDispatch(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT
   bool run_pull = !(A_mat_type == GrB_SPARSE && u_vec_type == GrB_SPARSE);
   if (!run_pull) {
     if (lb_mode == GrB_LOAD_BALANCE_MERGE) {
+      // w becomes a sparse vector only if the push really runs: on a hand-back
+      // its previous storage (and with it a dense w that accum combines into) must
+      // survive untouched, so the tag is restored below.
+      Storage w_before;
+      CHECK(w->getStorage(&w_before));
       CHECK(w->setStorage(GrB_SPARSE));
       // In the automatic mode the push may hand the call back when the frontier
       // owns too many of the edges (spmspv.hpp); both orientations must exist.
@@ -112,6 +117,7 @@ Info mxvDispatch(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT
       CHECK(spmspvMerge(&w->sparse_, mask, accum, op,
           &A->sparse_, &u->sparse_, desc, may_switch ? &prefer_pull : NULL));
       if (prefer_pull) {
+        w->vec_type_ = w_before;
         CHECK(u_t->sparse2dense(op.identity(), desc));
         run_pull = true;
       }

@@ -14,6 +14,7 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <boost/program_options.hpp>
 #include "graphblas/graphblas.hpp"
+#include "graphblas/backend/cuda/spmv_hub.hpp"
 
 bool debug_;
 bool memory_;
@@ -99,7 +100,54 @@ streamGatherKernel(float* out, const int* colind, const float* val,
   if (acc == 123.456f) out[0] = acc;
 }
 
+// Reference point 3: same as 2 but every column is folded into a window of
+// `mask`+1 elements: the gathers keep hitting distinct 128-byte lines (one L1
+// wavefront each) while the L2 sector traffic disappears (window resident in L1).
+template <int NT>
+__global__ void __launch_bounds__(NT)
+streamGatherWindowKernel(float* out, const int* colind, const float* val,
+                         const float* u, long long nnz, int mask) {
+  long long c = (long long)blockIdx.x*NT + threadIdx.x;
+  const long long stride = (long long)gridDim.x*NT;
+  const uint64_t pol = makeEvictLastPolicy();
+  float acc = 0.f;
+  for (; (c + 1)*8 <= nnz; c += stride) {
+    Word8 cw = ldStream256(colind + c*8);
+    Word8 vw = ldStream256(val + c*8);
+    float uv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) uv[j] = ldGather(u + (cw.w[j] & mask), pol);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fminf(acc, __int_as_float(vw.w[j]) + uv[j]);
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
 typedef graphblas::MinimumPlusSemiring<float> SR;
+
+template <int GROUPS, int HUB_K, int PF>
+float runHub(float* w, const HubIndex& h, const int* rowptr, const float* val,
+             const float* u, int n, int nnz, int reps) {
+  SR op;
+  thrust::device_vector<int> crow(h.ntiles);
+  thrust::device_vector<float> cval(h.ntiles);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(a, gbStream());
+    spmvHubRun<GROUPS, HUB_K, PF>(w, h, op, rowptr, val, u, n, nnz,
+        thrust::raw_pointer_cast(crow.data()), thrust::raw_pointer_cast(cval.data()),
+        gbStream());
+    cudaEventRecord(b, gbStream());
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) printf("CUDA error: %s\n", cudaGetErrorString(err));
+  return best;
+}
 
 template <int NT, int IPT, bool Gather, bool LaneMajor>
 float runMerge(float* w, const int* rowptr, const int* colind, const float* val,
@@ -216,6 +264,7 @@ int main(int argc, char** argv) {
              NT, IPT, (int)G, (int)LM, CARVE);                               \
     report(name, runMerge<NT, IPT, G, LM>(wp, rp, ci, va, up, (int)n,        \
                                           (int)nnz, reps, CARVE)); }
+  if (getenv("LAB_FULL")) {
   LAB(128, 7, true, false, 25)
   LAB(128, 9, true, false, 25)
   LAB(128, 11, true, false, 25)
@@ -228,5 +277,54 @@ int main(int argc, char** argv) {
   LAB(256, 9, true, false, 33)
   LAB(128, 9, true, true, 25)
   LAB(128, 9, false, false, 25)
+  } else { LAB(128, 9, true, false, 25) }
+
+  // wavefront vs sector: gathers folded into 4 KB / 64 KB / 1 MB windows
+  for (int mask : {1023, 16383, 262143}) {
+    best = 1e30f;
+    for (int r = 0; r < reps + 1; ++r) {
+      cudaEventRecord(a);
+      streamGatherWindowKernel<256><<<148*8, 256>>>(wp, ci, va, up, nnz, mask);
+      cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+      if (r > 0 && ms < best) best = ms;
+    }
+    char name[96];
+    snprintf(name, sizeof(name), "stream + gather folded into %d floats", mask + 1);
+    report(name, best);
+  }
+
+  // ---- hub kernel -------------------------------------------------------------
+  // reference result: the merge kernel
+  runMerge<128, 9, true, false>(wp, rp, ci, va, up, (int)n, (int)nnz, 1, 25);
+  std::vector<float> want(n), got(n);
+  cudaMemcpy(want.data(), wp, n*sizeof(float), cudaMemcpyDeviceToHost);
+  float* w2p = thrust::raw_pointer_cast(w2.data());
+  auto check = [&](const char* name) {
+    cudaMemcpy(got.data(), w2p, n*sizeof(float), cudaMemcpyDeviceToHost);
+    long long bad = 0; long long firstbad = -1;
+    for (size_t i = 0; i < n; ++i)
+      if (memcmp(&want[i], &got[i], 4) != 0) { if (!bad) firstbad = i; ++bad; }
+    printf("   %-40s %s (%lld mismatches, first %lld)\n", name,
+           bad ? "MISMATCH" : "bit-exact", bad, firstbad);
+    cudaMemset(w2p, 0xff, n*sizeof(float));
+  };
+#define HUBLAB(G, K, P)                                                        \
+  { HubIndex h;                                                                \
+    buildHubIndex(&h, rp, ci, (Index)n, (Index)n, (Index)nnz, K > 0 ? K : 4);  \
+    if (K == 0) cudaMemcpy(h.enc_ci, ci, nnz*sizeof(int), cudaMemcpyDeviceToDevice); \
+    char name[96];                                                             \
+    snprintf(name, sizeof(name), "hub groups=%d K=%d prefetch=%d cover=%.3f", G, K, P, \
+             K > 0 ? h.coverage : 0.0);                                        \
+    report(name, runHub<G, K, P>(w2p, h, rp, va, up, (int)n, (int)nnz, reps)); \
+    check(name);                                                               \
+    h.release(); }
+  HUBLAB(8, 32768, 0)
+  HUBLAB(8, 32768, 2)
+  HUBLAB(8, 32768, 4)
+  HUBLAB(8, 24576, 2)
+  HUBLAB(8, 16384, 2)
+  HUBLAB(6, 32768, 2)
+  HUBLAB(4, 32768, 2)
+  HUBLAB(8, 0, 2)
   return 0;
 }
