@@ -1,24 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the direction-optimised mxv/vxm path.
+"""bench.py — benchmark of the direction-optimised mxv/vxm path and its consumers.
 
-Metric (BASELINE.json): MTEPS = stored entries of A / time of one full traversal,
-direction-optimised BFS (LogicalOrAnd vxm, push SpMSpV <-> pull SpMV) on an R-MAT
-scale-24 edge-factor-16 graph (configs[2]), with the reference's benchmark flags
-(run_bfs.sh:8-27: --mxvmode 0 --struconly 1 --opreuse 1 --earlyexit 1).
-`--algo sssp` runs the MinimumPlus SSSP on the same graph instead
-(run_sssp.sh:15-32 flags), `--algo pr` PageRank, `--algo tc` triangle counting.
+Metric (BASELINE.json): MTEPS = stored entries of A / time of one full run of the
+algorithm.  Workloads (`--algo`, defaults are the BASELINE.json configs):
+  bfs   configs[2]  direction-optimised BFS (LogicalOrAnd vxm, push SpMSpV <-> pull
+                    SpMV), R-MAT scale 24 ef 16, reference flags of run_bfs.sh:8-27
+                    (--mxvmode 0 --struconly 1 --opreuse 1 --earlyexit 1)   [default]
+  sssp  configs[1]  MinimumPlus SSSP, R-MAT scale 22, pull-only SpMV (--mxvmode 2)
+  pr    configs[3]  PageRank (PlusMultiplies mxv), R-MAT-22 surrogate of
+                    soc-LiveJournal1 (not on disk, no network), 10 iterations
+  tc    configs[4]  triangle count (masked mxm on tril(A)), R-MAT scale 22
+`--scale` / `--mxvmode` override the config.  A "step" is one full run from the same
+source.  One JSON line on stdout:
+  value         device-timed, graph resident in HBM, K steps between CUDA events
+  e2e           the same run through the public API with host buffers: step input
+                H2D from pinned memory + run + D2H of the n-float result, every step
+  roofline      the dominant hot kernel: algorithmic bytes / CUDA-event
+                time of its launches, against the measured HBM peak
+  per_mxv       per hot kernel: launches, ms, edges touched per ms (§8d)
+  cpu_baseline  the reference's own CPU code (oracle/_ref) on one host core
+  parity_vs_cpu_reference   the GPU result against that CPU code (this file is the
+                only place that touches oracle/; the package never does)
 
-A "step" is one full traversal from the same source.  One JSON line on stdout:
-  value       device-timed, graph resident in HBM, K steps between CUDA events
-  e2e         the same traversal through the public API with a host result buffer:
-              source id H2D + traversal + D2H of the n-float result, every step
-  roofline    the dominant hot kernel: algorithmic bytes / CUDA-event time, against
-              the measured HBM peak in MEASURED_PEAKS.json
-  cpu_baseline  the reference's own CPU BFS (oracle/_ref) or the oracle port, one
-              traversal of the same graph on one host core
-
-`--impl reference` times the reference's CPU implementation of the same traversal
-instead (rank 0 only).
+`--impl reference` times the reference's CPU implementation instead (rank 0 only).
 """
 import argparse
 import json
@@ -33,6 +37,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# one unit string for every line this file (and graphblast_b200.dist) prints
+UNIT = "MTEPS (stored entries of A / traversal time x 1e-6)"
+
+DEFAULT_SCALE = {"bfs": 24, "sssp": 22, "pr": 22, "tc": 22}
+DEFAULT_MXVMODE = {"bfs": 0, "sssp": 2, "pr": 0, "tc": 0}
+PR_ITERATIONS = 10
+PR_ALPHA = 0.85
+PR_TOLERANCE = 1e-5          # north_star: relative, PageRank / SSSP
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -43,16 +56,19 @@ def parse_args():
     ap.add_argument("--algo", default="bfs", choices=["bfs", "sssp", "pr", "tc"])
     ap.add_argument("--scale", type=int, default=None,
                     help="R-MAT scale; default: GB200_BENCH_SCALE, else the scale "
-                         "BASELINE.json names for the algorithm (bfs/sssp 24, "
-                         "pr/tc 22)")
+                         "BASELINE.json names for the algorithm (bfs 24, others 22)")
+    ap.add_argument("--mxvmode", type=int, default=None, choices=[0, 1, 2],
+                    help="0 push-pull, 1 push only, 2 pull only (reference "
+                         "--mxvmode); default per config: bfs 0, sssp 2")
     ap.add_argument("--edgefactor", type=int, default=16)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.scale is None:
         env = os.environ.get("GB200_BENCH_SCALE")
-        args.scale = int(env) if env else {"bfs": 24, "sssp": 24, "pr": 22,
-                                           "tc": 22}[args.algo]
+        args.scale = int(env) if env else DEFAULT_SCALE[args.algo]
+    if args.mxvmode is None:
+        args.mxvmode = DEFAULT_MXVMODE[args.algo]
     return args
 
 
@@ -136,8 +152,8 @@ def measured_peak_hbm():
 def measured_traffic(args, kind):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
     kernel, from the committed `ncu --set full` capture of this workload
-    (profiles/traffic.json, written by tools/summarize_ncu.py traffic); None when
-    no capture of this (algo, scale, kernel) has been taken."""
+    (profiles/traffic.json); None when no capture of this (algo, scale, kernel)
+    has been taken."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         table = json.load(open(path))
@@ -146,7 +162,7 @@ def measured_traffic(args, kind):
         return None
 
 
-def build_graph(args, torch, gb, graphs):
+def build_graph(args, torch, graphs):
     """R-MAT on the device with the reference loader's semantics (undirected,
     no self-loops, no duplicates, sorted rows)."""
     n = 1 << args.scale
@@ -157,23 +173,150 @@ def build_graph(args, torch, gb, graphs):
     return n, rowptr, colind
 
 
-def cpu_bfs_baseline(h_rowptr, h_colind, source):
+# ---------------------------------------------------------------------------
+# The checker: the reference's CPU code (oracle/_ref, else the oracle port) on the
+# same graph.  Used by the single-GPU path below, by graphblast_b200.dist through
+# args.verify, and timed by --impl reference.
+# ---------------------------------------------------------------------------
+
+def _orc():
     import oracle_binding as orc
-    if orc.ref() is not None:
-        kind, fn = "reference", orc.ref_bfs
-    else:
-        kind, fn = "port", orc.bfs
-    t0 = time.perf_counter()
-    levels = fn(h_rowptr, h_colind, source)
-    dt = time.perf_counter() - t0
-    return kind, dt, levels
+    return orc, ("reference" if orc.ref() is not None else "port")
+
+
+def pagerank_fp64(h_rp, h_ci, alpha, niter):
+    """The iteration of reference test_pr.hpp:15-80 in float64 (the arithmetic
+    truth both float32 results are measured against)."""
+    import numpy as np
+    import scipy.sparse as sp
+    n = len(h_rp) - 1
+    A = sp.csr_matrix((np.ones(len(h_ci), dtype=np.float64), h_ci, h_rp), shape=(n, n))
+    outdeg = np.diff(h_rp).astype(np.float64)
+    p = np.full(n, 1.0 / n)
+    for _ in range(niter):
+        contrib = np.divide(p, outdeg, out=np.zeros(n), where=outdeg > 0)
+        p = (1.0 - alpha) / n + alpha * (A.T @ contrib)
+    return p
+
+
+def tc_golden(scale, nnz, h_ci):
+    """Committed triangle count of this exact graph (tests/golden/tc_golden.json,
+    counted once by the reference's SimpleReferenceTc), or None."""
+    import numpy as np
+    try:
+        table = json.load(open(os.path.join(ROOT, "tests", "golden", "tc_golden.json")))
+    except Exception:
+        return None
+    g = table.get("rmat%d" % scale)
+    if g is None or g["nnz"] != nnz:
+        return None
+    check = int(np.sum(h_ci.astype(np.int64) *
+                       (np.arange(len(h_ci), dtype=np.int64) % 97 + 1)))
+    return g if check == g["colind_checksum"] else None
+
+
+def tc_sample_rows(lr, budget_entries=3_000_000):
+    """Leading principal submatrix L[0:r, 0:r] with about budget_entries stored
+    entries: closed under the intersections of a triangle count on tril (every
+    neighbour of a row is a lower row), so it is a well-defined bounded sample of
+    the same workload for timing the sequential CPU code."""
+    import numpy as np
+    r = int(np.searchsorted(lr, budget_entries, side="left"))
+    return max(min(r, len(lr) - 1), 1)
+
+
+def verify(args, algo, h_rp, h_ci, got, ctx):
+    """(parity, cpu_baseline, extra) — got: the GPU result (levels / distances /
+    ranks as float32[n], or the triangle count)."""
+    import numpy as np
+    orc, kind = _orc()
+    nnz = int(len(h_ci))
+    extra = None
+    base = {"unit": "MTEPS", "cores": 1, "kind": kind,
+            "host_cores_total": os.cpu_count()}
+    if algo == "bfs":
+        fn = orc.ref_bfs if kind == "reference" else orc.bfs
+        t0 = time.perf_counter()
+        want = fn(h_rp, h_ci, ctx["source"])
+        dt = time.perf_counter() - t0
+        parity = bool(np.array_equal(np.asarray(got).astype(np.int32), want))
+        base.update(value=nnz / (dt * 1e6), ms=dt * 1e3,
+                    sample="one full BFS of the same graph from the same source")
+    elif algo == "sssp":
+        fn = orc.ref_sssp if kind == "reference" else orc.sssp
+        t0 = time.perf_counter()
+        want = fn(h_rp, h_ci, ctx["weights"], ctx["source"])
+        dt = time.perf_counter() - t0
+        parity = bool(np.array_equal(np.asarray(got), want))
+        base.update(value=nnz / (dt * 1e6), ms=dt * 1e3,
+                    sample="one full SSSP of the same graph from the same source")
+    elif algo == "pr":
+        fn = orc.ref_pr if kind == "reference" else orc.pr
+        alpha, niter = ctx["alpha"], ctx["niter"]
+        t0 = time.perf_counter()
+        want = fn(h_rp, h_ci, alpha, 0.0, niter)   # exactly the iterations the GPU ran
+        dt = time.perf_counter() - t0
+        truth = pagerank_fp64(h_rp, h_ci, alpha, niter)
+        got64 = np.asarray(got, dtype=np.float64)
+
+        def rel(x, y):
+            return float(np.max(np.abs(x - y) / np.maximum(np.abs(y), 1e-300)))
+        gpu_vs_ref = rel(got64, want.astype(np.float64))
+        gpu_vs_truth = rel(got64, truth)
+        ref_vs_truth = rel(want.astype(np.float64), truth)
+        # north_star: within 1e-5 relative of the reference.  Both sides compute the
+        # same float32 iteration with different summation orders; where the
+        # reference's own float32 error against the float64 iteration exceeds the
+        # tolerance (hub rows: >1e5 sequential float32 adds), agreement with the
+        # reference cannot be better than that error, so the test is: the GPU is
+        # within tolerance of the float64 iteration AND no further from the
+        # reference than the reference is from the float64 iteration (+ tolerance).
+        parity = bool(gpu_vs_truth <= PR_TOLERANCE and
+                      gpu_vs_ref <= ref_vs_truth + PR_TOLERANCE)
+        extra = {"tolerance": PR_TOLERANCE,
+                 "max_rel_err_vs_reference": gpu_vs_ref,
+                 "max_rel_err_vs_fp64_iteration": gpu_vs_truth,
+                 "reference_max_rel_err_vs_fp64_iteration": ref_vs_truth,
+                 "within_tolerance_of_reference": bool(gpu_vs_ref <= PR_TOLERANCE)}
+        base.update(value=nnz / (dt * 1e6), ms=dt * 1e3,
+                    sample="one full PageRank (%d iterations) of the same graph" % niter)
+    else:  # tc — ctx: lr, lc (host tril), scale
+        lr, lc = ctx["lr"], ctx["lc"]
+        fn = orc.ref_tc if kind == "reference" else orc.tc
+        g = tc_golden(ctx["scale"], nnz, h_ci)
+        if g is not None and ctx["scale"] > 18:
+            want = int(g["triangles_tril"])
+            r = tc_sample_rows(lr)
+            t0 = time.perf_counter()
+            fn(lr[:r + 1].copy(), lc[:lr[r]].copy())
+            dt = time.perf_counter() - t0
+            sample_nnz = 2 * int(lr[r])
+            base.update(value=sample_nnz / (dt * 1e6), ms=dt * 1e3,
+                        sample="triangle count of the leading %d rows of tril(A) "
+                               "(%d stored entries, a neighbour-closed part of the "
+                               "same graph); the full count (%d, %.0f s on one core) "
+                               "is the committed golden tests/golden/tc_golden.json"
+                               % (r, int(lr[r]), want, g["cpu_seconds"]))
+            extra = {"expected": want, "source": "tests/golden/tc_golden.json"}
+        else:
+            t0 = time.perf_counter()
+            want = int(fn(lr, lc))
+            dt = time.perf_counter() - t0
+            base.update(value=nnz / (dt * 1e6), ms=dt * 1e3,
+                        sample="one full triangle count of the same graph")
+            extra = {"expected": want, "source": "counted in this run"}
+            if g is not None:
+                extra["golden_agrees"] = bool(want == int(g["triangles_tril"]))
+        parity = bool(int(got) == want)
+    return parity, base, extra
 
 
 def run_reference_arm(args):
-    """The reference's CPU implementation (SimpleReferenceBfs / Sssp, built from
-    the reference sources into oracle/_ref; oracle port when that is absent) on
-    the same graph and source; one traversal per step, single host thread (the
-    reference's CPU code is sequential)."""
+    """The reference's CPU implementation (SimpleReferenceBfs / Sssp / Pr / Tc, built
+    from the reference sources into oracle/_ref; oracle port when that is absent) on
+    the same graph and source; one run per step, single host thread (the reference's
+    CPU code is sequential).  Triangle counting above scale 18 times a bounded,
+    neighbour-closed sample (tc_sample_rows) per step."""
     import numpy as np
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -181,27 +324,39 @@ def run_reference_arm(args):
         return
     import graphblast_b200 as gb
     from graphblast_b200 import graphs
-    import oracle_binding as orc
+    orc, kind = _orc()
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     gb.init(int(os.environ.get("LOCAL_RANK", "0")))
-    n, rowptr, colind = build_graph(args, torch, gb, graphs)
+    n, rowptr, colind = build_graph(args, torch, graphs)
     h_rp = rowptr.cpu().numpy()
     h_ci = colind.cpu().numpy()
     nnz = int(h_ci.shape[0])
     source = int(np.argmax(np.diff(h_rp)))
     del rowptr, colind
-    kind = "reference" if orc.ref() is not None else "port"
+    work = nnz
+    sample = ("one full run of the same algorithm on the same graph per step "
+              "(sequential code: 1 host thread)")
     if args.algo == "sssp":
         w = gb.api.host_uniform_weights(args.seed, 1, 64, nnz)
         step = (lambda: orc.ref_sssp(h_rp, h_ci, w, source)) if kind == "reference" \
             else (lambda: orc.sssp(h_rp, h_ci, w, source))
     elif args.algo == "pr":
-        step = (lambda: orc.ref_pr(h_rp, h_ci, 0.85, 0.0, 10)) if kind == "reference" \
-            else (lambda: orc.pr(h_rp, h_ci, 0.85, 0.0, 10))
+        step = (lambda: orc.ref_pr(h_rp, h_ci, PR_ALPHA, 0.0, PR_ITERATIONS)) \
+            if kind == "reference" \
+            else (lambda: orc.pr(h_rp, h_ci, PR_ALPHA, 0.0, PR_ITERATIONS))
     elif args.algo == "tc":
         lr, lc = orc.tril(h_rp, h_ci)        # the reference driver counts on tril(A)
-        step = (lambda: orc.ref_tc(lr, lc)) if kind == "reference" \
-            else (lambda: orc.tc(lr, lc))
+        fn = orc.ref_tc if kind == "reference" else orc.tc
+        if args.scale > 18:
+            r = tc_sample_rows(lr)
+            slr, slc = lr[:r + 1].copy(), lc[:lr[r]].copy()
+            work = 2 * int(lr[r])
+            sample = ("triangle count of the leading %d rows of tril(A), %d stored "
+                      "entries (a neighbour-closed part of the same graph; the full "
+                      "sequential count takes about an hour)" % (r, int(lr[r])))
+            step = lambda: fn(slr, slc)      # noqa: E731
+        else:
+            step = lambda: fn(lr, lc)        # noqa: E731
     else:
         step = (lambda: orc.ref_bfs(h_rp, h_ci, source)) if kind == "reference" \
             else (lambda: orc.bfs(h_rp, h_ci, source))
@@ -212,18 +367,16 @@ def run_reference_arm(args):
         step()
     dt = time.perf_counter() - t0
     ms = dt * 1e3 / args.steps
-    mteps = nnz / (ms * 1e3)
+    mteps = work / (ms * 1e3)
     out = {
         "impl": "reference",
-        "metric": "MTEPS", "value": mteps, "unit": "MTEPS (edges/s x 1e-6)",
+        "metric": "MTEPS", "value": mteps, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, n, nnz, source),
         "cpu_baseline": {"value": mteps, "unit": "MTEPS", "cores": 1,
-                         "kind": kind,
-                         "sample": "one full run of the same algorithm on the same "
-                                   "graph per step (sequential code: 1 host thread)"},
+                         "kind": kind, "sample": sample},
         "e2e": {"value": mteps, "unit": "MTEPS", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -232,18 +385,51 @@ def run_reference_arm(args):
 
 def workload_config(args, n, nnz, source):
     names = {"bfs": "direction-optimised BFS (LogicalOrAnd vxm, push<->pull)",
-             "sssp": "SSSP (MinimumPlus vxm, push<->pull)",
-             "pr": "PageRank (PlusMultiplies vxm, 10 iterations)",
+             "sssp": "SSSP (MinimumPlus vxm)",
+             "pr": "PageRank (PlusMultiplies vxm, %d iterations)" % PR_ITERATIONS,
              "tc": "triangle count (masked mxm on tril)"}
+    flags = "--mxvmode %d" % args.mxvmode
+    if args.algo == "bfs":
+        flags += " --struconly 1 --opreuse 1 --earlyexit 1"
     return {"workload": "%s on R-MAT scale-%d ef-%d (a,b,c,d)=(.57,.19,.19,.05) "
                         "seed %d, symmetrised, no self-loops/duplicates"
                         % (names[args.algo], args.scale, args.edgefactor,
                            args.seed),
-            "n": n, "nnz": nnz, "source": source,
-            "flags": "--mxvmode 0 --struconly 1 --opreuse 1 --earlyexit 1"
-                     if args.algo == "bfs" else "--mxvmode 0",
+            "n": n, "nnz": nnz, "source": source, "flags": flags,
             "l2_policy": "inputs larger than L2 (graph arrays >> 126 MB)",
             "partition": "1-D row slices" if args.gpus > 1 else "single GPU"}
+
+
+KINDS = ["spmvMergeKernel / spmvHubKernel (generic pull SpMV)",
+         "spmvMaskedOrPullKernel (fused Boolean pull)",
+         "spmspvPushKernel (push SpMSpV expand)",
+         "spgemmMaskedKernel (masked dot-product SpGEMM)"]
+
+
+def per_mxv_rates(args, prof, n, nnz):
+    """Edges touched per millisecond of every hot kernel, from the
+    algorithmic bytes the library accumulates per kind:
+      generic pull  : every stored entry, per launch;
+      Boolean pull  : (bytes - 12n - 4 per launch) / 4 = colind entries inspected;
+      push          : (bytes - frontier/output terms) / bytes per expanded edge
+                      (colind 4 + value 4 if key-value + mask lookup 4 if masked:
+                      8 for the BFS and SSSP pushes)."""
+    out = {}
+    for k, (ms, ln, by) in enumerate(prof):
+        if ln == 0:
+            continue
+        if k == 0:
+            edges = float(ln) * nnz
+        elif k == 1:
+            edges = max(by - ln * (12.0 * n + 4.0), 0.0) / 4.0
+        elif k == 2:
+            edges = by / 8.0
+        else:
+            edges = float(ln) * nnz
+        out[KINDS[k]] = {"launches": ln, "ms": ms, "alg_bytes": by,
+                         "edges_touched": edges,
+                         "edges_touched_per_ms": edges / ms if ms > 0 else None}
+    return out
 
 
 def main():
@@ -267,26 +453,30 @@ def main():
 
     if world > 1:
         from graphblast_b200 import dist as gdist
+        assert gdist.UNIT == UNIT
+        args.verify = lambda algo, rp, ci, got, ctx: verify(args, algo, rp, ci, got, ctx)
         result = gdist.bench_distributed(args, world, rank, local_rank)
         if rank == 0:
             print(json.dumps(result), flush=True)
         return
 
-    n, rowptr, colind = build_graph(args, torch, gb, graphs)
+    n, rowptr, colind = build_graph(args, torch, graphs)
     nnz = int(colind.numel())
     deg = rowptr[1:] - rowptr[:-1]
     source = int(torch.argmax(deg).item())
 
-    desc_flags = dict(mxvmode=0)
+    desc_flags = dict(mxvmode=args.mxvmode)
     if args.algo == "bfs":
         desc_flags.update(struconly=1, opreuse=1, earlyexit=1)
     if args.algo == "sssp":
         desc_flags.update(switchpoint=0.025)
     if args.algo == "pr":
-        desc_flags.update(max_niter=10)
+        desc_flags.update(max_niter=PR_ITERATIONS)
     desc = gb.Descriptor(**desc_flags)
 
     keep = []
+    w = None
+    h_tril = None
     if args.algo == "bfs":
         A = graphs.matrix_from_csr(n, rowptr, colind)
     elif args.algo in ("sssp", "pr"):
@@ -299,19 +489,13 @@ def main():
         A = graphs.matrix_from_csr(n, rowptr, colind, d_w, cscval=d_wt)
         keep += [d_w, d_wt]
         if args.algo == "pr":
-            A.pr_normalize(0.85, desc)
+            A.pr_normalize(PR_ALPHA, desc)
     else:
-        h_rp = rowptr.cpu().numpy()
-        h_ci = colind.cpu().numpy()
-        import oracle_binding as orc_build
-        lr, lc = orc_build.tril(h_rp, h_ci)
-        d_lr = torch.from_numpy(lr).cuda()
-        d_lc = torch.from_numpy(lc).cuda()
-        A = graphs.matrix_from_csr(n, d_lr, d_lc, dtype=gb.api.INT32,
-                                   symmetric=False,
-                                   cscval=torch.ones(len(lc), dtype=torch.int32,
-                                                     device="cuda"))
-        keep += [d_lr, d_lc]
+        # L = tril(A) through the library's own tril (reference gtc.cu:76-80)
+        A = graphs.matrix_from_csr(n, rowptr, colind, dtype=gb.api.INT32,
+                                   symmetric=True)
+        A.tril(desc)
+        h_tril = A.extract_csr()[:2]
         B = gb.Matrix(n, n, dtype=gb.api.INT32)
 
     result_vec = gb.Vector(n)
@@ -323,7 +507,7 @@ def main():
         elif args.algo == "sssp":
             algorithm.sssp(result_vec, A, source, desc)
         elif args.algo == "pr":
-            algorithm.pr(result_vec, A, 0.85, 1e-8, desc)
+            algorithm.pr(result_vec, A, PR_ALPHA, 0.0, desc)
         else:
             tc_count[0] = algorithm.tc(A, B, desc)[0]
 
@@ -354,10 +538,6 @@ def main():
     ms_per_step = total_ms / args.steps
     mteps = nnz / (ms_per_step * 1e3)
 
-    kinds = ["spmvMergeKernel (merge-path pull SpMV)",
-             "spmvMaskedOrPullKernel (fused Boolean pull)",
-             "spmspvPushKernel (push SpMSpV expand)",
-             "spgemmMaskedKernel (masked dot-product SpGEMM)"]
     prof = []
     for k in range(4):
         ms, ln, by = C.c_double(0), C.c_longlong(0), C.c_double(0)
@@ -369,7 +549,7 @@ def main():
     dom_ms, dom_launches, dom_bytes = prof[dom]
     achieved = (dom_bytes / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
     roofline = {
-        "kernel": kinds[dom], "bound": "hbm",
+        "kernel": KINDS[dom], "bound": "hbm",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak if peak else None,
         "peak_source": peak_src,
@@ -378,8 +558,6 @@ def main():
         "ms_per_launch": dom_ms / dom_launches if dom_launches else 0,
         "share_of_step": dom_ms / total_ms if total_ms else 0,
         "traffic": measured_traffic(args, dom),
-        "all_kernels": {kinds[k]: {"ms": prof[k][0], "launches": prof[k][1],
-                                   "alg_bytes": prof[k][2]} for k in range(4)},
     }
 
     # ---- end-to-end through the public API, host buffers -----------------------
@@ -409,68 +587,26 @@ def main():
            "d2h_bytes_per_step": 4 * n if args.algo != "tc" else 8,
            "note": "graph resident (built once, like the reference's "
                    "Matrix::build before its timed loop); per step: source id "
-                   "H2D, traversal, n-float result D2H into pinned memory"}
+                   "H2D, run, n-float result D2H into pinned memory"}
 
-    # ---- CPU baseline: the reference's own CPU code on one host core -------------
+    # ---- CPU baseline + parity: the reference's own CPU code on one host core -----
     cpu_baseline = None
     parity = None
+    extra = None
     if not args.no_cpu_baseline:
         h_rp = rowptr.cpu().numpy()
         h_ci = colind.cpu().numpy()
-        if args.algo == "bfs":
-            kind, dt, levels = cpu_bfs_baseline(h_rp, h_ci, source)
-            got = result_vec.extractTuples().astype(np.int32)
-            parity = bool(np.array_equal(got, levels))
-            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
-                            "cores": 1, "kind": kind, "ms": dt * 1e3,
-                            "host_cores_total": os.cpu_count(),
-                            "sample": "one full BFS of the same graph from the "
-                                      "same source"}
-        elif args.algo == "sssp":
-            import oracle_binding as orc
-            kind = "reference" if orc.ref() is not None else "port"
-            fn = orc.ref_sssp if kind == "reference" else orc.sssp
-            t0 = time.perf_counter()
-            dist = fn(h_rp, h_ci, w, source)
-            dt = time.perf_counter() - t0
-            parity = bool(np.array_equal(result_vec.extractTuples(), dist))
-            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
-                            "cores": 1, "kind": kind, "ms": dt * 1e3,
-                            "host_cores_total": os.cpu_count(),
-                            "sample": "one full SSSP of the same graph"}
-        elif args.algo == "pr":
-            import oracle_binding as orc
-            kind = "reference" if orc.ref() is not None else "port"
-            fn = orc.ref_pr if kind == "reference" else orc.pr
-            t0 = time.perf_counter()
-            want = fn(h_rp, h_ci, 0.85, 0.0, 10)   # exactly the 10 iterations the GPU ran
-            dt = time.perf_counter() - t0
+        if args.algo == "tc":
+            got = tc_count[0]
+            ctx = {"lr": h_tril[0], "lc": h_tril[1], "scale": args.scale}
+        else:
             got = result_vec.extractTuples()
-            rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)))
-            # float32 sums of >1e5 terms in two different orders: see DESIGN.md §5
-            parity = bool(rel <= 1e-4)
-            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
-                            "cores": 1, "kind": kind, "ms": dt * 1e3,
-                            "host_cores_total": os.cpu_count(),
-                            "max_rel_err": rel,
-                            "sample": "one full PageRank (10 iterations) of the "
-                                      "same graph"}
-        elif args.algo == "tc" and args.scale <= 20:
-            import oracle_binding as orc
-            kind = "reference" if orc.ref() is not None else "port"
-            fn = orc.ref_tc if kind == "reference" else orc.tc
-            t0 = time.perf_counter()
-            want = int(fn(lr, lc))          # the reference driver counts on tril(A)
-            dt = time.perf_counter() - t0
-            parity = bool(int(tc_count[0]) == want)
-            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
-                            "cores": 1, "kind": kind, "ms": dt * 1e3,
-                            "host_cores_total": os.cpu_count(),
-                            "sample": "one full triangle count of the same graph"}
+            ctx = {"source": source, "weights": w, "alpha": PR_ALPHA,
+                   "niter": PR_ITERATIONS}
+        parity, cpu_baseline, extra = verify(args, args.algo, h_rp, h_ci, got, ctx)
 
     out = {
-        "metric": "MTEPS", "value": mteps,
-        "unit": "MTEPS (stored entries of A / traversal time x 1e-6)",
+        "metric": "MTEPS", "value": mteps, "unit": UNIT,
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -480,11 +616,15 @@ def main():
         "e2e": e2e,
         "gpu_launches": int(launches1.value - launches0.value),
         "roofline": roofline,
+        "per_mxv": per_mxv_rates(args, prof, n, nnz),
         "cpu_baseline": cpu_baseline,
         "parity_vs_cpu_reference": parity,
     }
     if args.algo == "tc":
         out["triangles"] = int(tc_count[0])
+        out["triangle_check"] = extra
+    if args.algo == "pr":
+        out["pagerank_check"] = extra
     print(json.dumps(out), flush=True)
 
 

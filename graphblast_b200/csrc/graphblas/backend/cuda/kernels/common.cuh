@@ -72,23 +72,6 @@ __device__ __forceinline__ int ldGather32(const void* p, uint64_t pol) {
   return v;
 }
 
-// Gather that must not displace anything in L1 (cold tail of a relabelled vector).
-__device__ __forceinline__ int ldGatherCold32(const void* p, uint64_t pol) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
-               : "=r"(v) : "l"(p), "l"(pol));
-  return v;
-}
-
-template <typename T>
-__device__ __forceinline__ T ldGatherCold(const T* p, uint64_t pol) {
-  static_assert(sizeof(T) == 4, "32-bit element expected");
-  int bits = ldGatherCold32(p, pol);
-  T v;
-  memcpy(&v, &bits, 4);
-  return v;
-}
-
 template <typename T>
 __device__ __forceinline__ T ldGather(const T* p, uint64_t pol) {
   static_assert(sizeof(T) == 4, "32-bit element expected");

@@ -82,10 +82,7 @@ __global__ void spmvMergePartitionKernel(Index* __restrict__ tile_rows,
 // free, and the sequential readers pay one XOR.
 __device__ __forceinline__ int prodSlot(int p) { return p ^ ((p >> 3) & 4); }
 
-// Gather: 0 = no gather (lab only), 1 = gather u[col], 2 = gather with hot/cold
-// split (column ids relabelled by descending reference count: ids below hot_limit
-// may allocate in L1, the cold tail is loaded L1::no_allocate so it cannot evict
-// the hot prefix — experimental, GB200_SPMV_RELABEL).
+// Gather: 0 = no gather (lab only), 1 = gather u[col].
 template <int NT, int IPT, bool Vec256, int Gather, bool LaneMajor,
           typename W, typename a, typename U,
           typename MulOp, typename AddOp>
@@ -102,8 +99,7 @@ spmvMergeKernelT(W* __restrict__           w,
                 Index                     nnz,
                 W                         identity,
                 MulOp                     mul_op,
-                AddOp                     add_op,
-                Index                     hot_limit) {
+                AddOp                     add_op) {
   // One buffer: products grow from the bottom, row ends from the top.  A tile has
   // nr row ends and nk nonzeros with nr + nk <= NT*IPT, the product window adds at
   // most 14 slots of alignment slack and the row ends one entry (the open row).
@@ -181,10 +177,7 @@ spmvMergeKernelT(W* __restrict__           w,
       U uv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        uv[j] = (Gather == 2)
-                    ? (cw.w[j] < hot_limit ? ldGather(u + cw.w[j], pol)
-                                           : ldGatherCold(u + cw.w[j], pol))
-              : Gather ? ldGather(u + cw.w[j], pol)
+        uv[j] = Gather ? ldGather(u + cw.w[j], pol)
                        : static_cast<U>(cw.w[j] & 1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {

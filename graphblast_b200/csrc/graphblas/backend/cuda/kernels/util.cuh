@@ -170,41 +170,6 @@ frontierDegreeScanKernel(Index* __restrict__ offs,
   }
 }
 
-// ---- column relabelling for the generic pull SpMV (experimental, opt-in) --------
-// cnt[c] += 1 for every stored entry in column c
-__global__ void columnCountKernel(int* __restrict__ cnt,
-                                  const Index* __restrict__ colind, Index nnz) {
-  Index k = blockIdx.x*blockDim.x + threadIdx.x;
-  const Index stride = gridDim.x*blockDim.x;
-  for (; k < nnz; k += stride) atomicAdd(cnt + colind[k], 1);
-}
-
-// rank[perm[r]] = r
-__global__ void invertPermKernel(Index* __restrict__ rank,
-                                 const Index* __restrict__ perm, Index n) {
-  Index r = blockIdx.x*blockDim.x + threadIdx.x;
-  const Index stride = gridDim.x*blockDim.x;
-  for (; r < n; r += stride) rank[perm[r]] = r;
-}
-
-// out[k] = rank[colind[k]]
-__global__ void relabelKernel(Index* __restrict__ out,
-                              const Index* __restrict__ colind,
-                              const Index* __restrict__ rank, Index nnz) {
-  Index k = blockIdx.x*blockDim.x + threadIdx.x;
-  const Index stride = gridDim.x*blockDim.x;
-  for (; k < nnz; k += stride) out[k] = rank[colind[k]];
-}
-
-// out[r] = in[perm[r]]
-template <typename T>
-__global__ void permuteGatherKernel(T* __restrict__ out, const T* __restrict__ in,
-                                    const Index* __restrict__ perm, Index n) {
-  Index r = blockIdx.x*blockDim.x + threadIdx.x;
-  const Index stride = gridDim.x*blockDim.x;
-  for (; r < n; r += stride) out[r] = in[perm[r]];
-}
-
 // Posts one device-side Index to the host mailbox (backend/cuda/util.hpp).
 __global__ void postIndexKernel(const Index* __restrict__ value,
                                 unsigned long long* mail,

@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "graphblas/backend/cuda/util.hpp"
+#include "graphblas/backend/cuda/hub_index.hpp"
 
 namespace graphblas {
 namespace backend {
@@ -134,23 +135,16 @@ class SparseMatrix {
   Index*       d_pull_first_[2];
   const Index* pull_first_key_[2];
   Index        pull_first_nvals_[2];
-  // Optional (GB200_SPMV_RELABEL=1, experimental, off by default): a copy of the
-  // column indices relabelled by descending reference count, and the permutation
-  // that goes with it (relabel_perm_[r] = original id of the column ranked r), so
-  // that the generic pull SpMV gathers the hub columns from one contiguous,
-  // cache-resident prefix of a permuted copy of u.
-  Index*       d_relabel_ci_[2]   = {NULL, NULL};
-  Index*       d_relabel_perm_[2] = {NULL, NULL};
-  const Index* relabel_key_[2]    = {NULL, NULL};
-  Index        relabel_nvals_[2]  = {-1, -1};
+  // Hub index of the hub-cached pull SpMV (same indexing): which columns live in
+  // shared memory, encoded column array, compact non-empty rows, tile records.
+  // hub_state_: 0 = not built, 1 = built and used, 2 = built and rejected (too
+  // little of the matrix references the hub columns).
+  HubIndex     hub_[2];
+  int          hub_state_[2] = {0, 0};
   void dropSpmvTiles() {
     for (int k = 0; k < 2; ++k) {
-      if (d_relabel_ci_[k] != NULL) gbFree(d_relabel_ci_[k]);
-      if (d_relabel_perm_[k] != NULL) gbFree(d_relabel_perm_[k]);
-      d_relabel_ci_[k] = NULL;
-      d_relabel_perm_[k] = NULL;
-      relabel_key_[k] = NULL;
-      relabel_nvals_[k] = -1;
+      hub_[k].release();
+      hub_state_[k] = 0;
       if (d_pull_first_[k] != NULL) gbFree(d_pull_first_[k]);
       d_pull_first_[k] = NULL;
       pull_first_key_[k] = NULL;

@@ -16,6 +16,7 @@
 #include <string>
 
 #include "graphblas/backend/cuda/kernels/kernels.hpp"
+#include "graphblas/backend/cuda/spmv_hub.hpp"
 
 namespace graphblas {
 namespace backend {
@@ -25,7 +26,7 @@ namespace backend {
 template <typename W, typename a, typename U, typename SemiringT>
 Info spmvMergeLaunch(W* out, const Index* tile_rows, SemiringT op, const Index* rowptr,
     const Index* colind, const a* val, const U* u, Index nrows, Index nnz,
-    Descriptor* desc, Index hot_limit = 0) {
+    Descriptor* desc) {
   if (nrows <= 0) return GrB_SUCCESS;
   const long long total = static_cast<long long>(nrows) + nnz;
   const int nctas = static_cast<int>((total + GB_SPMV_TILE - 1)/GB_SPMV_TILE);
@@ -49,34 +50,45 @@ Info spmvMergeLaunch(W* out, const Index* tile_rows, SemiringT op, const Index* 
         cudaFuncAttributePreferredSharedMemoryCarveout, GB_SPMV_CARVEOUT);
     cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true, true, W, a, U, MulT, AddT>,
         cudaFuncAttributePreferredSharedMemoryCarveout, GB_SPMV_CARVEOUT);
-    cudaFuncSetAttribute(spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, 2, false, W, a, U, MulT, AddT>,
-        cudaFuncAttributePreferredSharedMemoryCarveout, GB_SPMV_CARVEOUT);
     configured = true;
   }
   // 1 = 256-bit loads, 8 consecutive nonzeros per thread (needs 32-byte aligned
   // arrays); 2 = 32-bit loads, lanes on consecutive nonzeros (any alignment).
   static const int load_mode = getEnv("GB200_SPMV_LOADS", 1);
-  if (hot_limit > 0 && aligned)        // relabelled columns: hot/cold gather split
-    spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, 2, false><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
-        carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
-        extractMul(op), extractAdd(op), hot_limit);
-  else if ((load_mode == 2 || !aligned) && sizeof(a) == 4)
+  if ((load_mode == 2 || !aligned) && sizeof(a) == 4)
     spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true, true><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
-        extractMul(op), extractAdd(op), 0);
+        extractMul(op), extractAdd(op));
   else if (aligned)
     spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, true, true, false><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
-        extractMul(op), extractAdd(op), 0);
+        extractMul(op), extractAdd(op));
   else
     spmvMergeKernelT<GB_SPMV_NT, GB_SPMV_IPT, false, true, false><<<nctas, GB_SPMV_NT, 0, s>>>(out, tile_rows, carry_row,
         carry_val, rowptr, colind, val, u, nrows, nnz, op.identity(),
-        extractMul(op), extractAdd(op), 0);
+        extractMul(op), extractAdd(op));
   GB_KERNEL_CHECK();
   spmvCarryFixupKernel<<<(nctas + 255)/256, 256, 0, s>>>(out, carry_row,
       carry_val, nctas, extractAdd(op));
   GB_KERNEL_CHECK();
   profiler().end(GB_PROF_SPMV_MERGE, s, alg_bytes);
+  return GrB_SUCCESS;
+}
+
+// Generic SpMV through the hub-cached kernel: 3 launches (pre-pass: hub values +
+// identity for the empty rows; the persistent SpMV kernel; carry fix-up).
+template <typename W, typename a, typename U, typename SemiringT>
+Info spmvHubLaunch(W* out, const HubIndex& h, SemiringT op, const a* val, const U* u,
+    Index nrows, Index nnz, Descriptor* desc) {
+  Index* carry_row = reinterpret_cast<Index*>(desc->scratch(
+      GB_SCRATCH_CARRY_ROW, static_cast<size_t>(h.ntiles)*sizeof(Index)));
+  W* carry_val = reinterpret_cast<W*>(desc->scratch(
+      GB_SCRATCH_CARRY_VAL, static_cast<size_t>(h.ntiles)*sizeof(W)));
+  cudaStream_t s = gbStream();
+  profiler().begin(GB_PROF_SPMV_MERGE, s);
+  spmvHubRun<GB_HUB_GROUPS, GB_HUB_CAPACITY>(out, h, op, val, u, nnz, carry_row,
+      carry_val, s);
+  profiler().end(GB_PROF_SPMV_MERGE, s, 8.0*nnz + 12.0*nrows + 4.0);
   return GrB_SUCCESS;
 }
 
@@ -284,78 +296,43 @@ Info spmv(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT o
       A_t->spmv_tiles_nvals_[which] = A->nvals_;
       A_t->spmv_tiles_count_[which] = ntiles;
     }
-    // Experimental, off by default (GB200_SPMV_RELABEL=1, read per call): gather
-    // from a copy of u permuted by descending column reference count through a
-    // relabelled copy of the column indices.  The products and their order are
-    // unchanged (results are bit-identical); only the gather addresses move, so
-    // that the hub columns sit in one contiguous, L1/L2-resident prefix.  Costs
-    // 4 bytes per stored entry of device memory and one n-element permutation
-    // pass per call.  Not measured in r01 (written after the GPU budget was spent).
-    const Index* gather_ci = A_csrColInd;
-    const U*     gather_u  = u_t->d_val_;
-    Index        hot_limit = 0;          // > 0: relabelled, ids below it may live in L1
-    {
-      const char* env = std::getenv("GB200_SPMV_RELABEL");
-      if (env != NULL && atoi(env) != 0 && A->nvals_ > 0 && sizeof(Index) == 4) {
+    // Large matrices whose entries mostly reference a few columns (power-law
+    // graphs) take the hub-cached kernel (kernels/spmv_hub.cuh): hub columns are
+    // served from shared memory, the rest as before.  The per-matrix index is
+    // built on first use; matrices where the hubs cover too little keep the
+    // merge kernel.  GB200_SPMV_HUB=0 forces the merge kernel.
+    bool done = false;
+    if (sizeof(W) == 4 && sizeof(a) == 4 && sizeof(U) == 4 && sizeof(Index) == 4) {
+      static const int hub_mode = getEnv("GB200_SPMV_HUB", 1);
+      static const int hub_min_nnz = getEnv("GB200_SPMV_HUB_MIN_NNZ", 1 << 22);
+      static const int hub_min_pct = getEnv("GB200_SPMV_HUB_MIN_PCT", 30);
+      const bool aligned32 =
+          (reinterpret_cast<uintptr_t>(A_csrColInd) % 32 == 0) &&
+          (reinterpret_cast<uintptr_t>(A_csrVal) % 32 == 0);
+      if (hub_mode != 0 && A->nvals_ >= hub_min_nnz && aligned32) {
         const Index ncols_t = use_tran ? A->nrows_ : A->ncols_;
-        if (A_t->d_relabel_ci_[which] == NULL ||
-            A_t->relabel_key_[which] != A_csrColInd ||
-            A_t->relabel_nvals_[which] != A->nvals_) {
-          if (A_t->d_relabel_ci_[which] != NULL) gbFree(A_t->d_relabel_ci_[which]);
-          if (A_t->d_relabel_perm_[which] != NULL) gbFree(A_t->d_relabel_perm_[which]);
-          A_t->d_relabel_ci_[which] = reinterpret_cast<Index*>(
-              gbMalloc(static_cast<size_t>(A->nvals_)*sizeof(Index)));
-          A_t->d_relabel_perm_[which] = reinterpret_cast<Index*>(
-              gbMalloc(static_cast<size_t>(ncols_t)*sizeof(Index)));
-          // scratch: counts, sorted counts, identity ids, rank
-          int*   cnt   = reinterpret_cast<int*>(gbMalloc(
-              static_cast<size_t>(ncols_t)*sizeof(int)));
-          int*   cnt_s = reinterpret_cast<int*>(gbMalloc(
-              static_cast<size_t>(ncols_t)*sizeof(int)));
-          Index* ids   = reinterpret_cast<Index*>(gbMalloc(
-              static_cast<size_t>(ncols_t)*sizeof(Index)));
-          Index* rank  = reinterpret_cast<Index*>(gbMalloc(
-              static_cast<size_t>(ncols_t)*sizeof(Index)));
-          CUDA_CALL(cudaMemsetAsync(cnt, 0, static_cast<size_t>(ncols_t)*sizeof(int), s));
-          columnCountKernel<<<gridFor(A->nvals_, 256, 8), 256, 0, s>>>(cnt,
-              A_csrColInd, A->nvals_);
-          GB_KERNEL_CHECK();
-          iotaKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(ids, ncols_t);
-          GB_KERNEL_CHECK();
-          size_t tmp_bytes = 0;
-          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(NULL, tmp_bytes, cnt, cnt_s, ids, A_t->d_relabel_perm_[which],
-              ncols_t, 0, 32, s));
-          void* tmp = gbMalloc(tmp_bytes);
-          CUDA_CALL(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, cnt, cnt_s, ids, A_t->d_relabel_perm_[which],
-              ncols_t, 0, 32, s));
-          invertPermKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(rank,
-              A_t->d_relabel_perm_[which], ncols_t);
-          GB_KERNEL_CHECK();
-          relabelKernel<<<gridFor(A->nvals_, 256, 8), 256, 0, s>>>(
-              A_t->d_relabel_ci_[which], A_csrColInd, rank, A->nvals_);
-          GB_KERNEL_CHECK();
-          gbFree(tmp); gbFree(rank); gbFree(ids); gbFree(cnt_s); gbFree(cnt);
-          A_t->relabel_key_[which]   = A_csrColInd;
-          A_t->relabel_nvals_[which] = A->nvals_;
+        HubIndex& h = A_t->hub_[which];
+        if (A_t->hub_state_[which] == 0 || h.key != A_csrColInd ||
+            h.key_nvals != A->nvals_) {
+          buildHubIndex(&h, A_csrRowPtr, A_csrColInd, A_nrows, ncols_t, A->nvals_,
+              GB_HUB_CAPACITY);
+          A_t->hub_state_[which] = (100.0*h.coverage >= hub_min_pct) ? 1 : 2;
+          if (A_t->hub_state_[which] == 2) {   // keep only the verdict
+            const Index* key = h.key; const Index key_nvals = h.key_nvals;
+            h.release();
+            h.key = key; h.key_nvals = key_nvals;
+          }
         }
-        U* u_perm = reinterpret_cast<U*>(desc->scratch(GB_SCRATCH_VEC_B,
-            static_cast<size_t>(ncols_t)*sizeof(U)));
-        permuteGatherKernel<<<gridFor(ncols_t, 256), 256, 0, s>>>(u_perm,
-            u_t->d_val_, A_t->d_relabel_perm_[which], ncols_t);
-        GB_KERNEL_CHECK();
-        gather_ci = A_t->d_relabel_ci_[which];
-        gather_u  = u_perm;
-        // Columns ranked below hot_limit are allowed to allocate in L1; the cold
-        // tail is loaded L1::no_allocate.  A sector-LRU simulation of one SM's
-        // gather stream on RMAT-22 gives 35 % L1 hits as is, 44 % relabelled with
-        // every gather allocating, and 58 % when only the top 48 K columns do.
-        const char* hot_env = std::getenv("GB200_SPMV_HOT");
-        hot_limit = (hot_env != NULL) ? atoi(hot_env) : 40960;
-        if (hot_limit < 1) hot_limit = 1;
+        if (A_t->hub_state_[which] == 1) {
+          CHECK(spmvHubLaunch(w_val, h, op, A_csrVal, u_t->d_val_, A_nrows,
+              A->nvals_, desc));
+          done = true;
+        }
       }
     }
-    CHECK(spmvMergeLaunch(w_val, A_t->d_spmv_tiles_[which], op, A_csrRowPtr, gather_ci,
-        A_csrVal, gather_u, A_nrows, A->nvals_, desc, hot_limit));
+    if (!done)
+    CHECK(spmvMergeLaunch(w_val, A_t->d_spmv_tiles_[which], op, A_csrRowPtr, A_csrColInd,
+        A_csrVal, u_t->d_val_, A_nrows, A->nvals_, desc));
 
     if (use_mask) {
       Storage mask_vec_type;

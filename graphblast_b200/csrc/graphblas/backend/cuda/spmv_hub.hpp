@@ -6,51 +6,31 @@
 #define GRAPHBLAS_BACKEND_CUDA_SPMV_HUB_HPP_
 
 #include "graphblas/backend/cuda/kernels/kernels.hpp"
+#include "graphblas/backend/cuda/hub_index.hpp"
 #include "graphblas/backend/cuda/kernels/spmv_hub.cuh"
 
 namespace graphblas {
 namespace backend {
 
-#define GB_HUB_GROUPS   4
+#define GB_HUB_GROUPS   8                // 128-thread groups per CTA (one CTA per SM)
 #define GB_HUB_CAPACITY 32768            // hub slots (x 4 bytes of shared memory)
 
-// Per (matrix, direction): which columns are hubs and the encoded column array.
-struct HubIndex {
-  Index*       enc_ci;      // [nnz] column id, or GB_HUB_FLAG | slot
-  Index*       hub_ids;     // [capacity] column id of every slot (first `count`)
-  void*        hub_vals;    // [capacity] x 4 bytes, refreshed per call
-  Index*       tile_rows;   // weighted merge-path partition: (rows, nonzeros) per boundary
-  int          ntiles;
-  int          count;       // slots in use
-  double       coverage;    // share of the stored entries that reference a hub
-  const Index* key;         // colind pointer this was built from
-  Index        key_nvals;
-  HubIndex() : enc_ci(NULL), hub_ids(NULL), hub_vals(NULL), tile_rows(NULL),
-               ntiles(0), count(0), coverage(0.), key(NULL), key_nvals(-1) {}
-  void release() {
-    if (enc_ci    != NULL) gbFree(enc_ci);
-    if (hub_ids   != NULL) gbFree(hub_ids);
-    if (hub_vals  != NULL) gbFree(hub_vals);
-    if (tile_rows != NULL) gbFree(tile_rows);
-    enc_ci = NULL; hub_ids = NULL; hub_vals = NULL; tile_rows = NULL;
-    ntiles = 0; count = 0; coverage = 0.; key = NULL; key_nvals = -1;
-  }
-};
-
 // Chooses the `capacity` most referenced columns (ties by arrival), assigns them
-// shared-memory slots and encodes the column array.  One-time cost per matrix:
-// a counting pass over colind, ~30 threshold probes over the n counts, two
-// assignment passes and the encoding pass.
+// shared-memory slots, encodes the column array, compacts the non-empty rows and
+// cuts the tiles.  One-time cost per matrix: a counting pass over colind, ~30
+// threshold probes over the n counts, the encoding pass, and a few passes over
+// rowptr.
 inline void buildHubIndex(HubIndex* h, const Index* rowptr, const Index* colind,
                           Index nrows, Index ncols, Index nnz, int capacity) {
   h->release();
   cudaStream_t s = gbStream();
   Runtime& rt = runtime();
+  h->capacity = capacity;
   int* cnt = reinterpret_cast<int*>(gbMalloc(static_cast<size_t>(ncols)*sizeof(int)));
   Index* slot = reinterpret_cast<Index*>(gbMalloc(static_cast<size_t>(ncols)*sizeof(Index)));
   unsigned long long* cells = reinterpret_cast<unsigned long long*>(
       gbMalloc(2*sizeof(unsigned long long)));
-  h->enc_ci   = reinterpret_cast<Index*>(gbMalloc(static_cast<size_t>(nnz)*sizeof(Index)));
+  h->enc_ci   = reinterpret_cast<Index*>(gbMalloc((static_cast<size_t>(nnz) + 8)*sizeof(Index)));
   h->hub_ids  = reinterpret_cast<Index*>(gbMalloc(static_cast<size_t>(capacity)*sizeof(Index)));
   h->hub_vals = gbMalloc(static_cast<size_t>(capacity)*4);
   CUDA_CALL(cudaMemsetAsync(cnt, 0, static_cast<size_t>(ncols)*sizeof(int), s));
@@ -81,28 +61,60 @@ inline void buildHubIndex(HubIndex* h, const Index* rowptr, const Index* colind,
   h->coverage = nnz > 0 ? static_cast<double>(covered)/static_cast<double>(nnz) : 0.;
   hubEncodeKernel<<<gridFor(nnz, 256, 8), 256, 0, s>>>(h->enc_ci, colind, slot, nnz);
   GB_KERNEL_CHECK();
+  gbFree(slot); gbFree(cnt);
+
+  // compact list of the non-empty rows
+  const int nblocks = static_cast<int>((static_cast<size_t>(nrows) + GB_HUB_CNT - 1)/GB_HUB_CNT);
+  Index* block_off = reinterpret_cast<Index*>(gbMalloc((static_cast<size_t>(nblocks) + 1)*sizeof(Index)));
+  Index* d_total = reinterpret_cast<Index*>(cells);
+  hubRowCountKernel<<<nblocks, GB_HUB_CNT, 0, s>>>(block_off, rowptr, nrows);
+  GB_KERNEL_CHECK();
+  hubRowScanKernel<<<1, GB_HUB_CNT, 0, s>>>(block_off, nblocks, d_total);
+  GB_KERNEL_CHECK();
+  h->m = rt.fetch(d_total);
+  h->nempty = nrows - h->m;
+  h->ne_ptr  = reinterpret_cast<Index*>(gbMalloc((static_cast<size_t>(h->m) + GB_HUB_PAD)*sizeof(Index)));
+  h->ne_rows = reinterpret_cast<Index*>(gbMalloc((static_cast<size_t>(h->m) + GB_HUB_PAD)*sizeof(Index)));
+  h->empty_rows = reinterpret_cast<Index*>(gbMalloc((static_cast<size_t>(h->nempty) + 1)*sizeof(Index)));
+  hubRowEmitKernel<<<nblocks, GB_HUB_CNT, 0, s>>>(h->ne_rows, h->ne_ptr, h->empty_rows,
+      block_off, rowptr, nrows);
+  GB_KERNEL_CHECK();
+  hubRowPadKernel<<<1, 32, 0, s>>>(h->ne_rows, h->ne_ptr, h->m, nnz);
+  GB_KERNEL_CHECK();
+  gbFree(block_off);
+
   // weighted merge-path partition (a row end weighs GB_HUB_RW items)
-  const long long total = static_cast<long long>(GB_HUB_RW)*nrows + nnz;
+  const long long total = static_cast<long long>(GB_HUB_RW)*h->m + nnz;
   h->ntiles = static_cast<int>((total + GB_HUB_TILE - 1)/GB_HUB_TILE);
   if (h->ntiles < 1) h->ntiles = 1;
-  h->tile_rows = reinterpret_cast<Index*>(
+  Index* bounds = reinterpret_cast<Index*>(
       gbMalloc(2*(static_cast<size_t>(h->ntiles) + 1)*sizeof(Index)));
-  hubPartitionKernel<<<(h->ntiles + 256)/256, 256, 0, s>>>(h->tile_rows,
-      rowptr, nrows, nnz, h->ntiles);
+  hubPartitionKernel<<<(h->ntiles + 256)/256, 256, 0, s>>>(bounds, h->ne_ptr, h->m,
+      nnz, h->ntiles);
   GB_KERNEL_CHECK();
-  gbFree(cells); gbFree(slot); gbFree(cnt);
+  h->desc = reinterpret_cast<int4*>(gbMalloc(static_cast<size_t>(h->ntiles)*sizeof(int4)));
+  hubTileDescKernel<<<(h->ntiles + 255)/256, 256, 0, s>>>(h->desc, bounds, h->ne_ptr,
+      h->m, h->ntiles);
+  GB_KERNEL_CHECK();
+  const size_t nchunks = (static_cast<size_t>(nnz) + 7)/8;
+  h->chunk_rel = reinterpret_cast<unsigned char*>(gbMalloc(nchunks + 16));
+  if (nnz > 0 && h->m > 0) {
+    hubChunkRowKernel<<<gridFor(nchunks, 256, 8), 256, 0, s>>>(h->chunk_rel, bounds,
+        h->ne_ptr, h->m, nnz, h->ntiles);
+    GB_KERNEL_CHECK();
+  }
+  gbFree(bounds); gbFree(cells);
   h->key = colind;
   h->key_nvals = nnz;
 }
 
 // w = A (+.x) u through the hub kernel.  carry_row / carry_val: ntiles entries.
-template <int GROUPS, int HUB_K, int PF, typename W, typename a, typename U, typename SemiringT>
-void spmvHubRun(W* out, const HubIndex& h, SemiringT op, const Index* rowptr,
-                const a* val, const U* u, Index nrows, Index nnz,
-                Index* carry_row, W* carry_val, cudaStream_t s) {
+template <int GROUPS, int HUB_K, typename W, typename a, typename U, typename SemiringT>
+void spmvHubRun(W* out, const HubIndex& h, SemiringT op, const a* val, const U* u,
+                Index nnz, Index* carry_row, W* carry_val, cudaStream_t s) {
   typedef decltype(extractMul(op)) MulT;
   typedef decltype(extractAdd(op)) AddT;
-  auto kern = spmvHubKernel<GROUPS, HUB_K, PF, W, a, U, MulT, AddT>;
+  auto kern = spmvHubKernel<GROUPS, HUB_K, W, a, U, MulT, AddT>;
   const HubSmemPlan plan = hubSmemPlan(GROUPS, HUB_K);
   static bool configured = false;        // once per instantiation
   if (!configured) {
@@ -110,20 +122,27 @@ void spmvHubRun(W* out, const HubIndex& h, SemiringT op, const Index* rowptr,
         cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total));
     configured = true;
   }
-  if (HUB_K > 0) {
-    hubGatherKernel<<<(HUB_K + 255)/256, 256, 0, s>>>(
+  const W identity = static_cast<W>(op.identity());
+  {
+    size_t work = static_cast<size_t>(h.nempty) > static_cast<size_t>(HUB_K)
+                      ? static_cast<size_t>(h.nempty) : static_cast<size_t>(HUB_K);
+    if (work < 1) work = 1;
+    hubPrepassKernel<<<gridFor(work, 256, 8), 256, 0, s>>>(
         reinterpret_cast<U*>(h.hub_vals), u, h.hub_ids, h.count, HUB_K,
-        static_cast<U>(op.identity()));
+        static_cast<U>(op.identity()), out, h.empty_rows, h.nempty, identity);
     GB_KERNEL_CHECK();
   }
   int grid = runtime().sm_count;
   const int need = (h.ntiles + GROUPS - 1)/GROUPS;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  kern<<<grid, GROUPS*GB_HUB_GT, plan.total, s>>>(out, h.tile_rows, carry_row,
-      carry_val, rowptr, h.enc_ci, val, u, reinterpret_cast<const U*>(h.hub_vals),
-      nrows, nnz, h.ntiles, static_cast<W>(op.identity()), extractMul(op),
-      extractAdd(op));
+  HubTiles tiles;
+  tiles.desc = h.desc; tiles.chunk_rel = h.chunk_rel;
+  tiles.ne_ptr = h.ne_ptr; tiles.ne_rows = h.ne_rows;
+  tiles.m = h.m; tiles.ntiles = h.ntiles;
+  kern<<<grid, GROUPS*GB_HUB_GT, plan.total, s>>>(out, tiles, carry_row, carry_val,
+      h.enc_ci, val, u, reinterpret_cast<const U*>(h.hub_vals), nnz, identity,
+      extractMul(op), extractAdd(op));
   GB_KERNEL_CHECK();
   spmvCarryFixupKernel<<<(h.ntiles + 255)/256, 256, 0, s>>>(out, carry_row,
       carry_val, h.ntiles, extractAdd(op));

@@ -28,6 +28,84 @@ import torch
 # Partition
 # ---------------------------------------------------------------------------
 
+# The one unit string of every bench line (both arms, every N): the driver divides
+# lines only when their units agree.
+UNIT = "MTEPS (stored entries of A / traversal time x 1e-6)"
+
+
+class _DevView(object):
+    """A raw device pointer as something torch.as_tensor understands."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {
+            "shape": (count,), "typestr": "<f4", "data": (int(ptr), False),
+            "version": 2}
+
+
+class ResultGather(object):
+    """End-to-end result path of the partitioned runs: the owned float slice of
+    every rank is gathered over NCCL into one n-float vector on rank 0's GPU and
+    copied into rank 0's pinned host buffer — the same 4n bytes of device->host
+    traffic per step as the single-GPU run."""
+
+    def __init__(self, bounds, world, rank, device):
+        self.bounds, self.world, self.rank, self.device = bounds, world, rank, device
+        self.sizes = [bounds[p + 1] - bounds[p] for p in range(world)]
+        self.pad = max(self.sizes)
+        self.n = bounds[world]
+        self.buf = torch.zeros(self.pad, dtype=torch.float32, device=device)
+        self.allv = torch.zeros(self.pad * world, dtype=torch.float32, device=device)
+        self.host = (torch.empty(self.n, dtype=torch.float32).pin_memory()
+                     if rank == 0 else None)
+
+    def run(self, vec):
+        """vec: gb.Vector holding this rank's owned slice.  Returns the host buffer
+        on rank 0 (valid after the call), None elsewhere."""
+        import torch.distributed as dist
+        nl = self.sizes[self.rank]
+        if nl > 0:
+            view = torch.as_tensor(_DevView(vec.device_ptr(), nl), device=self.device)
+            self.buf[:nl].copy_(view)
+        dist.all_gather_into_tensor(self.allv, self.buf)
+        if self.rank == 0:
+            for p in range(self.world):
+                if self.sizes[p]:
+                    self.host[self.bounds[p]:self.bounds[p + 1]].copy_(
+                        self.allv[p * self.pad:p * self.pad + self.sizes[p]],
+                        non_blocking=True)
+            torch.cuda.synchronize()
+            return self.host
+        return None
+
+    d2h_bytes = property(lambda self: 4 * self.n)
+
+
+def timed_e2e(args, step, gather, vec, dev, h2d_bytes):
+    """K steps through the public call path with host buffers: per step the step's
+    input goes host->device from pinned memory, the traversal runs, and the full
+    n-float result lands in rank 0's pinned host memory.  Wall clock, max over
+    ranks.  Returns (ms per step, e2e dict without the value)."""
+    import time
+    import torch.distributed as dist
+    host_in = torch.zeros(max(h2d_bytes // 4, 1), dtype=torch.int32).pin_memory()
+    dev_in = torch.zeros_like(host_in, device=dev)
+    for _ in range(2):
+        step()
+        gather.run(vec)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_in.copy_(host_in, non_blocking=True)
+        step()
+        gather.run(vec)
+    torch.cuda.synchronize()
+    wall = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    return float(wall.item()) / args.steps
+
+
+
 def partition_bounds(rowptr, world, align=1024):
     """Contiguous vertex ranges with (nearly) equal numbers of stored entries;
     every boundary is a multiple of `align` (>= 32, so bitmap slices are whole
@@ -439,40 +517,24 @@ def bench_distributed(args, world, rank, local_rank):
     lib.gb200_launch_count(C.byref(launches1))
     ms_per_step = float(ms[0].item()) / args.steps
 
-    # parity: gather the owned level slices on rank 0 and compare with the CPU code
-    mine = torch.from_numpy(ops.levels().astype(np.float32)).to(dev)
-    sizes = [bounds[p + 1] - bounds[p] for p in range(world)]
-    pad = max(sizes)
-    buf = torch.zeros(pad, dtype=torch.float32, device=dev)
-    buf[:mine.numel()] = mine
-    allv = torch.zeros(pad * world, dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(allv, buf)
+    # end to end: source id H2D, traversal, full level vector to rank 0's host memory
+    gather = ResultGather(bounds, world, rank, dev)
+    e2e_ms = timed_e2e(args, traverse, gather, ops.v, dev, 4)
+    # parity: the gathered result against the CPU code (the checker lives in
+    # bench.py: nothing in this package touches oracle/)
+    host = gather.run(ops.v)
     parity = None
     cpu_baseline = None
     nnz_per_rank = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
     gathered = [torch.zeros_like(nnz_per_rank) for _ in range(world)]
     dist.all_gather(gathered, nnz_per_rank)
-    if rank == 0:
-        got = np.concatenate([allv[p * pad:p * pad + sizes[p]].cpu().numpy()
-                              for p in range(world)]).astype(np.int32)
-        if not args.no_cpu_baseline:
-            import sys
-            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
-                os.path.abspath(__file__))), "tests"))
-            import oracle_binding as orc
-            kind = "reference" if orc.ref() is not None else "port"
-            fn = orc.ref_bfs if kind == "reference" else orc.bfs
-            t0 = time.perf_counter()
-            want = fn(h_rowptr, h_colind, source)
-            dt = time.perf_counter() - t0
-            parity = bool(np.array_equal(got, want))
-            cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS",
-                            "cores": 1, "kind": kind, "ms": dt * 1e3,
-                            "host_cores_total": os.cpu_count(),
-                            "sample": "one full BFS of the same graph"}
+    verify = getattr(args, "verify", None)
+    if rank == 0 and verify is not None and not args.no_cpu_baseline:
+        parity, cpu_baseline, _ = verify("bfs", h_rowptr, h_colind, host.numpy(),
+                                         {"source": source})
     result = {
         "metric": "MTEPS", "value": nnz / (ms_per_step * 1e3),
-        "unit": "MTEPS (stored entries of A / traversal time x 1e-6)",
+        "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -497,11 +559,12 @@ def bench_distributed(args, world, rank, local_rank):
                      "--mxvmode 0 --struconly 1 --earlyexit 1 (opreuse off: the "
                      "visited mask is local)",
             "l2_policy": "inputs larger than L2"},
-        "e2e": {"value": nnz / (float(ms[1].item()) / args.steps * 1e3),
-                "unit": "MTEPS", "h2d_bytes_per_step": 4,
-                "d2h_bytes_per_step": 8 * world,
-                "note": "host wall clock around the same K steps (max over "
-                        "ranks), including the per-level count read-back"},
+        "e2e": {"value": nnz / (e2e_ms * 1e3), "unit": "MTEPS",
+                "ms_per_step": e2e_ms, "h2d_bytes_per_step": 4,
+                "d2h_bytes_per_step": gather.d2h_bytes,
+                "note": "per step: source id H2D, traversal, NCCL gather of the "
+                        "owned level slices to rank 0 and the n-float result D2H "
+                        "into rank 0's pinned memory; wall clock, max over ranks"},
         "gpu_launches": int(launches1.value - launches0.value),
         "cpu_baseline": cpu_baseline,
         "parity_vs_cpu_reference": parity,
@@ -615,36 +678,19 @@ def bench_distributed_pr(args, world, rank, local_rank):
     kern_all = [torch.zeros_like(kern) for _ in range(world)]
     dist.all_gather(kern_all, kern)
 
-    mine = torch.from_numpy(p_own.extractTuples()[:nl].astype(np.float32)).to(dev)
-    sizes = [bounds[q + 1] - bounds[q] for q in range(world)]
-    pad = max(sizes)
-    buf = torch.zeros(pad, dtype=torch.float32, device=dev)
-    buf[:mine.numel()] = mine
-    allv = torch.zeros(pad * world, dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(allv, buf)
+    gather = ResultGather(bounds, world, rank, dev)
+    e2e_ms = timed_e2e(args, lambda: xchg.pr(p_own, M, n, alpha, 0.0, desc), gather,
+                       p_own, dev, 4)
+    host = gather.run(p_own)
     parity = None
     max_rel = None
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
-            os.path.abspath(__file__))), "tests"))
-        import oracle_binding as orc
-        got = np.concatenate([allv[q * pad:q * pad + sizes[q]].cpu().numpy()
-                              for q in range(world)])
-        kind = "reference" if orc.ref() is not None else "port"
-        fn = orc.ref_pr if kind == "reference" else orc.pr
-        t0 = time.perf_counter()
-        want = fn(h_rowptr, h_colind, alpha, 0.0, niter)
-        dt = time.perf_counter() - t0
-        max_rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)))
-        # 1e-5 is asserted by the tests at sizes whose rows are short; at bench
-        # sizes hub rows add >1e5 float terms and the CPU code accumulates them
-        # sequentially in float32, so the two summation orders agree to ~1e-4.
-        parity = bool(max_rel <= 1e-4)
-        cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS", "cores": 1,
-                        "kind": kind, "ms": dt * 1e3,
-                        "host_cores_total": os.cpu_count(),
-                        "sample": "one full PageRank (10 iterations) of the same graph"}
+    pr_check = None
+    verify = getattr(args, "verify", None)
+    if rank == 0 and verify is not None and not args.no_cpu_baseline:
+        parity, cpu_baseline, pr_check = verify("pr", h_rowptr, h_colind, host.numpy(),
+                                                {"alpha": alpha, "niter": niter})
+        max_rel = pr_check.get("max_rel_err_vs_reference") if pr_check else None
     from json import loads
     peak = None
     try:
@@ -657,7 +703,7 @@ def bench_distributed_pr(args, world, rank, local_rank):
     ach = max(float(k[1].item()) for k in kern_all) / (slow * 1e-3) / 1e9 if slow > 0 else 0.0
     result = {
         "metric": "MTEPS", "value": nnz / (ms_per_step * 1e3),
-        "unit": "MTEPS (stored entries of A / time of one PageRank run x 1e-6)",
+        "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -672,10 +718,12 @@ def bench_distributed_pr(args, world, rank, local_rank):
                         "rank's replica (CUDA IPC over NVLink) + residual partial "
                         "per iteration, loop in C++",
             "l2_policy": "inputs larger than L2"},
-        "e2e": {"value": nnz / (float(ms[1].item()) / args.steps * 1e3),
-                "unit": "MTEPS", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 8 * niter,
-                "note": "host wall clock around the same K steps (max over ranks)"},
+        "e2e": {"value": nnz / (e2e_ms * 1e3), "unit": "MTEPS",
+                "ms_per_step": e2e_ms, "h2d_bytes_per_step": 4,
+                "d2h_bytes_per_step": gather.d2h_bytes,
+                "note": "per step: one PageRank run, NCCL gather of the owned rank "
+                        "slices to rank 0 and the n-float result D2H into rank 0's "
+                        "pinned memory; wall clock, max over ranks"},
         "gpu_launches": int(launches1.value - launches0.value),
         "roofline": {"kernel": "spmvMergeKernel (merge-path pull SpMV), slowest rank",
                      "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -683,7 +731,7 @@ def bench_distributed_pr(args, world, rank, local_rank):
                      "ms_per_launch": slow},
         "cpu_baseline": cpu_baseline,
         "parity_vs_cpu_reference": parity,
-        "max_rel_err": max_rel, "parity_tolerance": 1e-4,
+        "max_rel_err": max_rel, "pagerank_check": pr_check,
         "clocks": clocks,
     }
     xchg.close()
@@ -787,31 +835,16 @@ def bench_distributed_sssp(args, world, rank, local_rank):
     kern_all = [torch.zeros_like(kern) for _ in range(world)]
     dist.all_gather(kern_all, kern)
 
-    mine = torch.from_numpy(v_own.extractTuples()[:nl].astype(np.float32)).to(dev)
-    sizes = [bounds[q + 1] - bounds[q] for q in range(world)]
-    pad = max(sizes)
-    buf = torch.zeros(pad, dtype=torch.float32, device=dev)
-    buf[:mine.numel()] = mine
-    allv = torch.zeros(pad * world, dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(allv, buf)
+    gather = ResultGather(bounds, world, rank, dev)
+    e2e_ms = timed_e2e(args, lambda: xchg.sssp(v_own, M, n, source, desc), gather,
+                       v_own, dev, 4)
+    host = gather.run(v_own)
     parity = None
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
-            os.path.abspath(__file__))), "tests"))
-        import oracle_binding as orc
-        got = np.concatenate([allv[q * pad:q * pad + sizes[q]].cpu().numpy()
-                              for q in range(world)])
-        kind = "reference" if orc.ref() is not None else "port"
-        fn = orc.ref_sssp if kind == "reference" else orc.sssp
-        t0 = time.perf_counter()
-        want = fn(h_rowptr, h_colind, w, source)
-        dt = time.perf_counter() - t0
-        parity = bool(np.array_equal(got, want))
-        cpu_baseline = {"value": nnz / (dt * 1e6), "unit": "MTEPS", "cores": 1,
-                        "kind": kind, "ms": dt * 1e3,
-                        "host_cores_total": os.cpu_count(),
-                        "sample": "one full SSSP of the same graph"}
+    verify = getattr(args, "verify", None)
+    if rank == 0 and verify is not None and not args.no_cpu_baseline:
+        parity, cpu_baseline, _ = verify("sssp", h_rowptr, h_colind, host.numpy(),
+                                         {"source": source, "weights": w})
     slow = max(kern_all, key=lambda k: float(k[0].item()))
     s_ms, s_n, s_b = (float(slow[0].item()), float(slow[1].item()),
                       float(slow[2].item()))
@@ -819,7 +852,7 @@ def bench_distributed_sssp(args, world, rank, local_rank):
     ach = (s_b / 1e9) / (s_ms / 1e3) if s_ms > 0 else 0.0
     result = {
         "metric": "MTEPS", "value": nnz / (ms_per_step * 1e3),
-        "unit": "MTEPS (stored entries of A / traversal time x 1e-6)",
+        "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -834,10 +867,12 @@ def bench_distributed_sssp(args, world, rank, local_rank):
                         "rank's replica (CUDA IPC over NVLink) + improved count per "
                         "round, loop in C++",
             "l2_policy": "inputs larger than L2"},
-        "e2e": {"value": nnz / (float(ms[1].item()) / args.steps * 1e3),
-                "unit": "MTEPS", "h2d_bytes_per_step": 8,
-                "d2h_bytes_per_step": 8 * max(rounds, 1),
-                "note": "host wall clock around the same K steps (max over ranks)"},
+        "e2e": {"value": nnz / (e2e_ms * 1e3), "unit": "MTEPS",
+                "ms_per_step": e2e_ms, "h2d_bytes_per_step": 4,
+                "d2h_bytes_per_step": gather.d2h_bytes,
+                "note": "per step: source id H2D, traversal, NCCL gather of the "
+                        "owned distance slices to rank 0 and the n-float result D2H "
+                        "into rank 0's pinned memory; wall clock, max over ranks"},
         "gpu_launches": int(launches1.value - launches0.value),
         "roofline": {"kernel": "spmvMergeKernel (merge-path pull SpMV), slowest rank",
                      "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",

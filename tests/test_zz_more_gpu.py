@@ -1,19 +1,19 @@
-"""GPU tests written after the round's GPU budget was spent (so they have not run on a
-device yet); kept in a file that sorts last so that, should one of them uncover a bug,
-`pytest -x` has already gone through the rest of the suite."""
+"""Further GPU tests: accum path, edge-share hand-back, advisor regressions
+(bitmap tail bits of fill(), storage of w on a hand-back), and the hub-cached
+pull SpMV forced onto the small graphs of the parity suite."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
 import oracle_binding as orc
 from test_parity_gpu import make_matrix, ragged_graph
 
-# Non-strict xfail until their first run on a device has been looked at: a pass is
-# reported as XPASS, a failure as XFAIL, and the suite's verdict stays what the
-# verified tests say.  (r02: drop the mark once these show XPASS.)
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False,
-                                reason="written after the r01 GPU budget was spent; "
-                                       "never executed on a device yet")]
+pytestmark = [pytest.mark.gpu]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -112,3 +112,88 @@ def test_column_relabelling_is_bit_identical(gb, name):
             os.environ["GB200_SPMV_RELABEL"] = "0"
     assert np.array_equal(out["0"][0].view(np.uint32), out["1"][0].view(np.uint32))
     assert np.array_equal(out["0"][0].view(np.uint32), out["1"][1].view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [11, 33, 64, 1000])
+def test_fill_then_push_when_size_is_not_a_multiple_of_32(gb, n):
+    """fill(1) builds the bitmap shadow; the bits past n in the last word must stay
+    clear, otherwise dense2sparse emits indices >= n (r01 advisor finding)."""
+    rng = np.random.RandomState(n)
+    src = rng.randint(0, n, 4*n).astype(np.int32)
+    dst = rng.randint(0, n, 4*n).astype(np.int32)
+    rp, ci = orc.build_csr(n, src, dst, True)
+    A = make_matrix(gb, rp, ci)
+    for sem in (gb.Semiring.PlusMultiplies, gb.Semiring.LogicalOrAnd):
+        u = gb.Vector(n)
+        u.fill(1.0)
+        w = gb.Vector(n)
+        gb.vxm(w, None, None, sem, u, A, gb.Descriptor(mxvmode=1))   # push only
+        want, _ = orc.vxm(int(sem), rp, ci, np.ones(len(ci), np.float32),
+                          np.ones(n, np.float32))
+        got = w.extractTuples()
+        assert got.shape[0] == n
+        assert np.array_equal(got, want)
+    u = gb.Vector(n)
+    u.fill(1.0)
+    import ctypes as C
+    import torch
+    from graphblast_b200 import _lib
+    d_bits = torch.zeros((n + 31)//32 + 1, dtype=torch.int32, device="cuda")
+    count = C.c_longlong(-1)
+    assert _lib.load().gb200_vector_export_bits(
+        u._h, C.c_void_p(d_bits.data_ptr()), C.byref(count)) == 0
+    assert count.value == n
+    words = d_bits.cpu().numpy().view(np.uint32)[:(n + 31)//32]
+    assert int(np.unpackbits(words.view(np.uint8)).sum()) == n
+
+
+def _run_parity_subset_with_hub_forced(kexpr):
+    env = dict(os.environ)
+    env.update(GB200_SPMV_HUB="1", GB200_SPMV_HUB_MIN_NNZ="0",
+               GB200_SPMV_HUB_MIN_PCT="0")
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
+           os.path.join(ROOT, "tests", "test_parity_gpu.py"), "-k", kexpr]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert " passed" in r.stdout
+
+
+def test_hub_spmv_on_the_parity_suite_semirings():
+    """Every generic pull of the semiring sweep / gvxm cases through the hub-cached
+    kernel (kernels/spmv_hub.cuh): thresholds lowered so the small graphs take it."""
+    _run_parity_subset_with_hub_forced("semiring_sweep or gvxm or mxv_matches")
+
+
+def test_hub_spmv_on_the_parity_suite_algorithms():
+    _run_parity_subset_with_hub_forced("sssp or pagerank")
+
+
+@pytest.mark.parametrize("scale", [14, 16, 18, 20])
+def test_triangle_count_matches_the_committed_reference_counts(gb, scale):
+    """tests/golden/tc_golden.json holds the counts the reference's own CPU code
+    (SimpleReferenceTc, reference test_tc.hpp:15-85) produced for the R-MAT bench
+    graphs; the masked mxm must reproduce them exactly, through the library's own
+    tril (reference gtc.cu:76-82)."""
+    import json
+    import torch
+    from graphblast_b200 import algorithm, graphs
+    table = json.load(open(os.path.join(ROOT, "tests", "golden", "tc_golden.json")))
+    g = table["rmat%d" % scale]
+    n = 1 << scale
+    src, dst = graphs.rmat_edges(scale, 16, seed=1)
+    rowptr, colind = graphs.build_csr(n, src, dst, undirected=True)
+    assert int(colind.numel()) == g["nnz"]
+    h_ci = colind.cpu().numpy()
+    check = int(np.sum(h_ci.astype(np.int64) *
+                       (np.arange(len(h_ci), dtype=np.int64) % 97 + 1)))
+    assert check == g["colind_checksum"]
+    desc = gb.Descriptor(mxvmode=0)
+    A = graphs.matrix_from_csr(n, rowptr, colind, dtype=gb.api.INT32, symmetric=True)
+    A.tril(desc)
+    assert A.nvals() == g["nnz_tril"]
+    B = gb.Matrix(n, n, dtype=gb.api.INT32)
+    ntris, _ = algorithm.tc(A, B, desc)
+    assert int(ntris) == g["triangles_tril"]
+    del A, B
+    torch.cuda.empty_cache()
