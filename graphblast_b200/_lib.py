@@ -39,6 +39,13 @@ SIGNATURES = [
     ("gb200_matrix_build_coo", _I, [_P, _P, _P, _P, _I, _I]),
     ("gb200_matrix_load_mtx", _I, [C.POINTER(_P), _I, _S, _I]),
     ("gb200_matrix_adopt_csr", _I, [_P, _P, _P, _P, _I]),
+    ("gb200_matrix_build_coo_device", _I, [_P, _P, _P, _P, _LL, _I]),
+    ("gb200_ingest_coo", _I, [_I, _I, _P, _P, _P, _LL, _I, C.POINTER(_P),
+                              C.POINTER(_LL)]),
+    ("gb200_ingest_export", _I, [_P, _P, _P, _P]),
+    ("gb200_ingest_free", _I, [_P]),
+    ("gb200_csr_transpose_values", _I, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    ("gb200_sort_pairs_u64", _I, [_P, _P, _LL, _I]),
     ("gb200_matrix_adopt_csc", _I, [_P, _P, _P, _P, _I]),
     ("gb200_matrix_nrows", _I, [_P, _IP]),
     ("gb200_matrix_ncols", _I, [_P, _IP]),

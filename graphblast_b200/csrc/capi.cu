@@ -45,6 +45,15 @@ struct gb200_matrix_s {
   graphblas::Matrix<int>*   i;
 };
 
+// Result of gb200_ingest_coo: a CSR in pool memory until exported / freed.
+struct gb200_ingest_s {
+  int nrows;
+  graphblas::Index nnz;
+  graphblas::Index* rowptr;
+  graphblas::Index* colind;
+  float* val;
+};
+
 namespace {
 
 using graphblas::Info;
@@ -332,21 +341,38 @@ int gb200_matrix_build_coo(gb200_matrix_t A, const int* h_rows,
 }  // extern "C"
 
 namespace {
+// Matrix Market file -> matrix: the text is parsed on the host (MtxFile), the raw
+// tuples go to the device, and symmetrising, ordering and the removal of
+// self-loops / repeated pairs run there (backend/cuda/ingest.hpp) with the
+// semantics of the reference's readMtx (graphblas/util.hpp:264-329, 364-430).
 template <typename T>
 Info loadMtx(graphblas::Matrix<T>** out, const char* path, int directed) {
+  using namespace graphblas::backend;
+  MtxFile file(path);
+  if (!file.ok) return graphblas::GrB_INVALID_VALUE;
   std::vector<graphblas::Index> rows, cols;
   std::vector<T> vals;
-  graphblas::Index nrows, ncols, nvals;
-  readMtx(path, &rows, &cols, &vals, &nrows, &ncols, &nvals, directed, false);
-  graphblas::Matrix<T>* M = new graphblas::Matrix<T>(nrows, ncols);
-  // Undirected decision as readMtx takes it (util.hpp:392-395).
-  FILE* f = fopen(path, "r");
-  MM_typecode code;
-  mm_read_banner(f, &code);
-  fclose(f);
-  bool undirected = (mm_is_symmetric(code) || directed == 2) && directed != 1;
-  M->matrix_.sparse_.symmetric_ = undirected;
-  Info info = M->build(&rows, &cols, &vals, nvals, GrB_NULL);
+  file.tuples<T>(&rows, &cols, &vals);
+  const bool undirected = directed != 1 && (file.symmetric() || directed == 2);
+  const bool drop_loops = getEnv("GRB_UTIL_REMOVE_SELFLOOP", true);
+  graphblas::Matrix<T>* M = new graphblas::Matrix<T>(file.nrows, file.ncols);
+  const size_t m = rows.size();
+  const size_t alloc = m > 0 ? m : 1;
+  graphblas::Index* d_r = reinterpret_cast<graphblas::Index*>(gbMalloc(alloc*sizeof(graphblas::Index)));
+  graphblas::Index* d_c = reinterpret_cast<graphblas::Index*>(gbMalloc(alloc*sizeof(graphblas::Index)));
+  T* d_v = reinterpret_cast<T*>(gbMalloc(alloc*sizeof(T)));
+  if (m > 0) {
+    CUDA_CALL(cudaMemcpyAsync(d_r, rows.data(), m*sizeof(graphblas::Index), cudaMemcpyHostToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_c, cols.data(), m*sizeof(graphblas::Index), cudaMemcpyHostToDevice, gbStream()));
+    CUDA_CALL(cudaMemcpyAsync(d_v, vals.data(), m*sizeof(T), cudaMemcpyHostToDevice, gbStream()));
+    runtime().sync();
+  }
+  const int mode = (undirected ? GB_INGEST_SYMMETRIZE : 0) |
+                   (drop_loops ? GB_INGEST_DROP_LOOPS : 0) | GB_INGEST_DEDUP;
+  M->matrix_.mat_type_ = graphblas::GrB_SPARSE;
+  Info info = M->matrix_.sparse_.buildFromDeviceTuples(d_r, d_c, d_v,
+      static_cast<long long>(m), mode, undirected);
+  gbFree(d_v); gbFree(d_c); gbFree(d_r);
   if (info != GrB_SUCCESS) {
     delete M;
     return info;
@@ -378,6 +404,126 @@ int gb200_matrix_load_mtx(gb200_matrix_t* out, int dtype, const char* path,
     return rc(info);
   }
   *out = m;
+  return 0;
+}
+
+int gb200_matrix_build_coo_device(gb200_matrix_t A, const int* d_rows,
+                                  const int* d_cols, const void* d_vals,
+                                  long long ntuples, int flags) {
+  if (A == NULL || (ntuples > 0 && (d_rows == NULL || d_cols == NULL)))
+    return rc(graphblas::GrB_NULL_POINTER);
+  if (ntuples < 0) return rc(graphblas::GrB_INVALID_VALUE);
+  GB200_REQUIRE_DEVICE();
+  const int mode = flags & 7;
+  const bool symmetric = (flags & GB200_INGEST_SYMMETRIC_STRUCTURE) != 0;
+  if (A->f) {
+    A->f->matrix_.mat_type_ = graphblas::GrB_SPARSE;
+    return rc(A->f->matrix_.sparse_.buildFromDeviceTuples(d_rows, d_cols,
+        static_cast<const float*>(d_vals), ntuples, mode, symmetric));
+  }
+  A->i->matrix_.mat_type_ = graphblas::GrB_SPARSE;
+  return rc(A->i->matrix_.sparse_.buildFromDeviceTuples(d_rows, d_cols,
+      static_cast<const int*>(d_vals), ntuples, mode, symmetric));
+}
+
+int gb200_ingest_coo(int nrows, int ncols, const int* d_rows, const int* d_cols,
+                     const float* d_vals, long long ntuples, int flags,
+                     gb200_ingest_t* out, long long* nnz) {
+  if (out == NULL || nnz == NULL || (ntuples > 0 && (d_rows == NULL || d_cols == NULL)))
+    return rc(graphblas::GrB_NULL_POINTER);
+  if (nrows <= 0 || ncols <= 0 || ntuples < 0) return rc(graphblas::GrB_INVALID_VALUE);
+  GB200_REQUIRE_DEVICE();
+  gb200_ingest_s* h = new gb200_ingest_s();
+  h->nrows = nrows;
+  h->nnz = graphblas::backend::ingestCooToCsr<float>(nrows, ncols, d_rows, d_cols,
+      d_vals, ntuples, flags & 7, &h->rowptr, &h->colind, &h->val);
+  *out = h;
+  *nnz = h->nnz;
+  return 0;
+}
+
+int gb200_ingest_export(gb200_ingest_t h, int* d_rowptr, int* d_colind, float* d_val) {
+  if (h == NULL) return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  cudaStream_t s = graphblas::backend::gbStream();
+  if (d_rowptr != NULL)
+    CUDA_CALL(cudaMemcpyAsync(d_rowptr, h->rowptr, (static_cast<size_t>(h->nrows) + 1)*sizeof(int),
+        cudaMemcpyDeviceToDevice, s));
+  if (d_colind != NULL && h->nnz > 0)
+    CUDA_CALL(cudaMemcpyAsync(d_colind, h->colind, static_cast<size_t>(h->nnz)*sizeof(int),
+        cudaMemcpyDeviceToDevice, s));
+  if (d_val != NULL && h->nnz > 0)
+    CUDA_CALL(cudaMemcpyAsync(d_val, h->val, static_cast<size_t>(h->nnz)*sizeof(float),
+        cudaMemcpyDeviceToDevice, s));
+  graphblas::backend::runtime().sync();
+  return 0;
+}
+
+int gb200_ingest_free(gb200_ingest_t h) {
+  if (h == NULL) return 0;
+  graphblas::backend::gbFree(h->val);
+  graphblas::backend::gbFree(h->colind);
+  graphblas::backend::gbFree(h->rowptr);
+  delete h;
+  return 0;
+}
+
+int gb200_csr_transpose_values(int nrows, int ncols, int nnz, const int* d_rowptr,
+                               const int* d_colind, const float* d_val,
+                               int* d_colptr_out, int* d_rowind_out,
+                               float* d_cscval_out) {
+  if (d_rowptr == NULL || d_colind == NULL || d_val == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  using namespace graphblas::backend;
+  graphblas::Index* colptr = NULL; graphblas::Index* rowind = NULL; float* cval = NULL;
+  ingestCsrToCsc<float>(nrows, ncols, nnz, d_rowptr, d_colind, d_val,
+      d_colptr_out != NULL ? &colptr : NULL, d_rowind_out != NULL ? &rowind : NULL,
+      d_cscval_out != NULL ? &cval : NULL);
+  cudaStream_t s = gbStream();
+  if (colptr != NULL) {
+    CUDA_CALL(cudaMemcpyAsync(d_colptr_out, colptr, (static_cast<size_t>(ncols) + 1)*sizeof(int), cudaMemcpyDeviceToDevice, s));
+    gbFree(colptr);
+  }
+  if (rowind != NULL) {
+    if (nnz > 0) CUDA_CALL(cudaMemcpyAsync(d_rowind_out, rowind, static_cast<size_t>(nnz)*sizeof(int), cudaMemcpyDeviceToDevice, s));
+    gbFree(rowind);
+  }
+  if (cval != NULL) {
+    if (nnz > 0) CUDA_CALL(cudaMemcpyAsync(d_cscval_out, cval, static_cast<size_t>(nnz)*sizeof(float), cudaMemcpyDeviceToDevice, s));
+    gbFree(cval);
+  }
+  runtime().sync();
+  return 0;
+}
+
+int gb200_sort_pairs_u64(unsigned long long* d_keys, unsigned int* d_payload,
+                         long long n, int bits) {
+  if (d_keys == NULL) return rc(graphblas::GrB_NULL_POINTER);
+  if (n < 0 || bits < 1 || bits > 64) return rc(graphblas::GrB_INVALID_VALUE);
+  GB200_REQUIRE_DEVICE();
+  using namespace graphblas::backend;
+  const size_t alloc = n > 0 ? static_cast<size_t>(n) : 1;
+  unsigned long long* keys = d_keys;
+  unsigned int* pay = d_payload;
+  unsigned long long* keys_tmp = reinterpret_cast<unsigned long long*>(gbMalloc(alloc*8));
+  unsigned int* pay_tmp = d_payload != NULL
+      ? reinterpret_cast<unsigned int*>(gbMalloc(alloc*4)) : NULL;
+  radixSortPairs(&keys, d_payload != NULL ? &pay : NULL, &keys_tmp,
+      d_payload != NULL ? &pay_tmp : NULL, n, bits);
+  cudaStream_t s = gbStream();
+  if (keys != d_keys) {              // an odd number of passes left the result in the temporaries
+    CUDA_CALL(cudaMemcpyAsync(d_keys, keys, alloc*8, cudaMemcpyDeviceToDevice, s));
+    if (d_payload != NULL)
+      CUDA_CALL(cudaMemcpyAsync(d_payload, pay, alloc*4, cudaMemcpyDeviceToDevice, s));
+    runtime().sync();
+    gbFree(keys);
+    if (pay != NULL && pay != d_payload) gbFree(pay);
+  } else {
+    runtime().sync();
+    gbFree(keys_tmp);
+    if (pay_tmp != NULL) gbFree(pay_tmp);
+  }
   return 0;
 }
 

@@ -1,8 +1,10 @@
-"""Graph ingest on the device (SURVEY.md §8f-1): R-MAT generation and
-COO -> CSR/CSC construction with the reference loader's semantics
+"""Graph ingest on the device (SURVEY.md §8 f1): R-MAT generation and
+tuples -> CSR / CSC construction with the reference loader's semantics
 (graphblas/util.hpp:264-329: symmetrise, drop self-loops and duplicates, sort
-row-major), using torch for sort/unique plumbing and the native library for the
-edge generator.  Results are checked against oracle/ in tests/.
+row-major).  Everything here runs in the native library's own kernels
+(csrc/graphblas/backend/cuda/ingest.hpp: radix sort of packed keys, scans,
+compaction); torch only owns the buffers.  Results are checked against oracle/ in
+tests/.
 """
 import ctypes as C
 
@@ -10,6 +12,15 @@ import torch
 
 from . import _lib
 from .api import _check, Matrix, FP32, INT32
+
+INGEST_SYMMETRIZE = 1
+INGEST_DROP_LOOPS = 2
+INGEST_DEDUP = 4
+INGEST_SYMMETRIC_STRUCTURE = 8
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
 def rmat_edges(scale, edgefactor=16, seed=1, device="cuda"):
@@ -19,51 +30,46 @@ def rmat_edges(scale, edgefactor=16, seed=1, device="cuda"):
     src = torch.empty(nedges, dtype=torch.int32, device=device)
     dst = torch.empty(nedges, dtype=torch.int32, device=device)
     _check(_lib.load().gb200_rmat_edges(int(scale), int(nedges), int(seed), 0,
-                                        C.c_void_p(src.data_ptr()),
-                                        C.c_void_p(dst.data_ptr())),
+                                        _p(src), _p(dst)),
            "gb200_rmat_edges")
     return src, dst
 
 
-def build_csr(n, src, dst, undirected=True):
+def build_csr(n, src, dst, undirected=True, val=None, return_values=False):
     """Loader semantics on the device.  Returns (rowptr int32[n+1],
-    colind int32[nnz]) as device tensors, rows sorted, no loops, no duplicates."""
-    s = src.to(torch.int64)
-    d = dst.to(torch.int64)
-    if undirected:
-        keep = s != d
-        keys = torch.cat([s * n + d, (d * n + s)[keep]])
-    else:
-        keys = s * n + d
-    del s, d
-    keys = keys[(keys // n) != (keys % n)]          # drop self-loops
-    keys = torch.unique(keys)                       # sorted + deduplicated
-    rows = keys // n
-    colind = (keys % n).to(torch.int32)
-    del keys
-    counts = torch.bincount(rows, minlength=n)
-    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=src.device)
-    torch.cumsum(counts, 0, out=rowptr[1:])
-    return rowptr.to(torch.int32), colind.contiguous()
+    colind int32[nnz]) as device tensors — rows sorted, no loops, no duplicates —
+    plus the float32 values of the kept tuples when return_values is set."""
+    lib = _lib.load()
+    flags = INGEST_DROP_LOOPS | INGEST_DEDUP | (INGEST_SYMMETRIZE if undirected else 0)
+    handle = C.c_void_p()
+    nnz = C.c_longlong(0)
+    _check(lib.gb200_ingest_coo(int(n), int(n), _p(src), _p(dst), _p(val),
+                                int(src.numel()), flags, C.byref(handle),
+                                C.byref(nnz)), "gb200_ingest_coo")
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=src.device)
+    colind = torch.empty(max(nnz.value, 1), dtype=torch.int32, device=src.device)
+    values = (torch.empty(max(nnz.value, 1), dtype=torch.float32, device=src.device)
+              if return_values else None)
+    try:
+        _check(lib.gb200_ingest_export(handle, _p(rowptr), _p(colind), _p(values)),
+               "gb200_ingest_export")
+    finally:
+        lib.gb200_ingest_free(handle)
+    colind = colind[:nnz.value]
+    if return_values:
+        return rowptr, colind, values[:nnz.value]
+    return rowptr, colind
 
 
 def transpose_values(n, rowptr, colind, val):
     """Values of the CSC of a structurally symmetric CSR: cscVal such that the
     entry stored at position k of "column j" (= row j of the symmetric pattern)
     holds A(colind[k], j)."""
-    nnz = colind.numel()
-    rows = torch.repeat_interleave(
-        torch.arange(n, device=colind.device, dtype=torch.int64),
-        (rowptr[1:] - rowptr[:-1]).to(torch.int64))
-    # position of (i, j) in row-major order is k; (j, i) sits at perm[k]
-    key_t = colind.to(torch.int64) * n + rows
-    order = torch.argsort(key_t)
-    del key_t, rows
-    # sorted transposed keys enumerate the same pattern in row-major order, so
-    # cscVal[pos] = val[order[pos]]
-    out = val[order]
-    assert out.numel() == nnz
-    return out.contiguous()
+    out = torch.empty_like(val)
+    _check(_lib.load().gb200_csr_transpose_values(
+        int(n), int(n), int(colind.numel()), _p(rowptr), _p(colind), _p(val),
+        None, None, _p(out)), "gb200_csr_transpose_values")
+    return out
 
 
 def matrix_from_csr(n, rowptr, colind, val=None, dtype=FP32, symmetric=True,

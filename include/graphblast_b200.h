@@ -95,15 +95,49 @@ int gb200_desc_get_knob(gb200_desc_t desc, const char* name, double* value);  /*
 /* ---- Matrix: reference graphblas/matrix.hpp:14-252 ---------------------- */
 int gb200_matrix_new(gb200_matrix_t* out, int dtype, int nrows, int ncols);   /* Matrix(nrows,ncols) :20 */
 int gb200_matrix_free(gb200_matrix_t A);
-/* Matrix::build from host COO triples (:125-144): builds CSR+CSC on the host and
- * uploads.  `undirected` plays the role of the ".ud." cache name (structurally
- * symmetric: CSC index arrays alias CSR on the device). */
+/* Matrix::build from host COO triples (:125-144): the triples are uploaded and
+ * ordered into CSR + CSC on the device.  `undirected` plays the role of the ".ud."
+ * cache name (structurally symmetric: CSC index arrays alias CSR on the device). */
 int gb200_matrix_build_coo(gb200_matrix_t A, const int* h_rows, const int* h_cols,
                            const void* h_vals, int nvals, int undirected);
 /* readMtx + Matrix::build, the loader path of every reference driver
- * (graphblas/util.hpp:364-430; example/gbfs.cu:57-69).  directed: 0/1/2. */
+ * (graphblas/util.hpp:364-430; example/gbfs.cu:57-69).  directed: 0/1/2.  The file
+ * is parsed on the host; symmetrising, ordering and the removal of self-loops and
+ * repeated entries run on the device with the loader's semantics. */
 int gb200_matrix_load_mtx(gb200_matrix_t* out, int dtype, const char* path,
                           int directed);
+/* ---- graph ingest on the device (no reference counterpart: the reference sorts
+ * tuple vectors on the host, graphblas/util.hpp:170-195, 264-329, 502-600) --------
+ * flags: the GB200_INGEST_* bits. */
+#define GB200_INGEST_SYMMETRIZE          1   /* add (col,row) of every non-loop tuple */
+#define GB200_INGEST_DROP_LOOPS          2   /* drop row == col */
+#define GB200_INGEST_DEDUP               4   /* keep the first of equal (row,col) */
+#define GB200_INGEST_SYMMETRIC_STRUCTURE 8   /* result is structurally symmetric:
+                                                CSC index arrays alias the CSR */
+/* Builds A (CSR + CSC, owned by A) from tuples in DEVICE memory; d_vals may be
+ * NULL (value 1) and has A's element type otherwise. */
+int gb200_matrix_build_coo_device(gb200_matrix_t A, const int* d_rows,
+                                  const int* d_cols, const void* d_vals,
+                                  long long ntuples, int flags);
+/* Tuples -> sorted CSR held by the library; *nnz says how much room
+ * gb200_ingest_export needs (d_rowptr[nrows+1], d_colind[nnz], d_val[nnz], any
+ * of them NULL to skip). */
+typedef struct gb200_ingest_s* gb200_ingest_t;
+int gb200_ingest_coo(int nrows, int ncols, const int* d_rows, const int* d_cols,
+                     const float* d_vals, long long ntuples, int flags,
+                     gb200_ingest_t* out, long long* nnz);
+int gb200_ingest_export(gb200_ingest_t h, int* d_rowptr, int* d_colind, float* d_val);
+int gb200_ingest_free(gb200_ingest_t h);
+/* CSC of a device CSR (csr2csc, reference graphblas/util.hpp:580-600); output
+ * pointers may be NULL to skip that array. */
+int gb200_csr_transpose_values(int nrows, int ncols, int nnz, const int* d_rowptr,
+                               const int* d_colind, const float* d_val,
+                               int* d_colptr_out, int* d_rowind_out,
+                               float* d_cscval_out);
+/* Stable LSD radix sort of 64-bit keys by their low `bits` bits, with an optional
+ * 32-bit payload, in place (the sort the ingest is built on; exported for tests). */
+int gb200_sort_pairs_u64(unsigned long long* d_keys, unsigned int* d_payload,
+                         long long n, int bits);
 /* Matrix::build(Index* row_ptr, Index* col_ind, T* values, Index nvals) (:152-161):
  * adopts DEVICE CSR arrays. */
 int gb200_matrix_adopt_csr(gb200_matrix_t A, int* d_rowptr, int* d_colind,
