@@ -406,7 +406,7 @@ KINDS = ["spmvMergeKernel / spmvHubKernel (generic pull SpMV)",
          "spgemmMaskedKernel (masked dot-product SpGEMM)"]
 
 
-def per_mxv_rates(args, prof, n, nnz):
+def per_mxv_rates(args, prof, n, nnz, fused=None):
     """Edges touched per millisecond of every hot kernel, from the
     algorithmic bytes the library accumulates per kind:
       generic pull  : every stored entry, per launch;
@@ -420,6 +420,10 @@ def per_mxv_rates(args, prof, n, nnz):
             continue
         if k == 0:
             edges = float(ln) * nnz
+        elif k == 1 and fused is not None:
+            # one launch per traversal: inspected + pushed entries of the last
+            # traversal (every traversal from the same source does the same work)
+            edges = float(ln) * (fused[1] + fused[4])
         elif k == 1:
             edges = max(by - ln * (12.0 * n + 4.0), 0.0) / 4.0
         elif k == 2:
@@ -544,6 +548,13 @@ def main():
         lib.gb200_profile_read(k, C.byref(ms), C.byref(ln), C.byref(by))
         prof.append((ms.value, ln.value, by.value))
     lib.gb200_profile_enable(0)
+    fused_stats = None
+    if args.algo == "bfs":
+        st = (C.c_ulonglong * 6)()
+        lib.gb200_bfs_stats(desc._h, n, st)
+        if st[0] > 0:
+            fused_stats = [int(x) for x in st]
+            KINDS[1] = "bfsFusedKernel (whole traversal: Boolean pull + push levels)"
     dom = max(range(4), key=lambda k: prof[k][0])
     peak, peak_src = measured_peak_hbm()
     dom_ms, dom_launches, dom_bytes = prof[dom]
@@ -559,6 +570,10 @@ def main():
         "share_of_step": dom_ms / total_ms if total_ms else 0,
         "traffic": measured_traffic(args, dom),
     }
+    if fused_stats is not None:
+        roofline["fused_traversal"] = dict(zip(
+            ["levels", "entries_inspected_pulling", "pull_levels", "vertices_pushed",
+             "edges_pushed", "discovered_pushing"], fused_stats))
 
     # ---- end-to-end through the public API, host buffers -----------------------
     host_out = torch.empty(n, dtype=torch.float32).pin_memory()
@@ -616,7 +631,7 @@ def main():
         "e2e": e2e,
         "gpu_launches": int(launches1.value - launches0.value),
         "roofline": roofline,
-        "per_mxv": per_mxv_rates(args, prof, n, nnz),
+        "per_mxv": per_mxv_rates(args, prof, n, nnz, fused_stats),
         "cpu_baseline": cpu_baseline,
         "parity_vs_cpu_reference": parity,
     }

@@ -85,6 +85,7 @@ SIGNATURES = [
     ("gb200_reduce_matrix", _I, [C.POINTER(_D), _I, _P, _P]),
     ("gb200_reduce_matrix_rows", _I, [_P, _I, _P, _P]),
     ("gb200_bfs", _I, [_P, _P, _I, _P, C.POINTER(_F)]),
+    ("gb200_bfs_stats", _I, [_P, _I, _P]),
     ("gb200_sssp", _I, [_P, _P, _I, _P, C.POINTER(_F)]),
     ("gb200_pr", _I, [_P, _P, _F, _F, _P, C.POINTER(_F)]),
     ("gb200_tc", _I, [C.POINTER(_LL), _P, _P, _P, C.POINTER(_F)]),

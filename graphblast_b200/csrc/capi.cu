@@ -954,6 +954,13 @@ int gb200_bfs(gb200_vector_t v, gb200_matrix_t A, int source, gb200_desc_t desc,
   return 0;
 }
 
+int gb200_bfs_stats(gb200_desc_t desc, int n, unsigned long long* out6) {
+  if (desc == NULL || out6 == NULL) return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  graphblas::backend::bfsFusedStats(&desc->desc.descriptor_, n, out6);
+  return 0;
+}
+
 int gb200_sssp(gb200_vector_t v, gb200_matrix_t A, int source,
                gb200_desc_t desc, float* tight_ms) {
   if (v == NULL || A == NULL || desc == NULL)

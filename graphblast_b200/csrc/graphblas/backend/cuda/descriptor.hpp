@@ -38,6 +38,7 @@ enum ScratchSlot {
   GB_SCRATCH_VEC_B,
   GB_SCRATCH_CUB,         // cub temp storage
   GB_SCRATCH_LOOKBACK,    // compaction: ticket cell + per-CTA look-back status
+  GB_SCRATCH_BFS,         // fused BFS: visited x2, frontier, next bitmaps + cells
   GB_SCRATCH_NSLOTS
 };
 
@@ -109,6 +110,7 @@ class Descriptor {
     }
     return slot_ptr_[slot];
   }
+  size_t scratchSize(ScratchSlot slot) const { return slot_size_[slot]; }
 
   // Look-back state of the single-pass compaction: cell 0 is a ticket counter
   // that only ever grows, cells 1..nblocks hold (epoch, flag, value) words.  The

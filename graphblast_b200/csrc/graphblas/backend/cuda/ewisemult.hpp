@@ -79,9 +79,21 @@ Info eWiseMultInner(SparseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
   Storage mask_type = GrB_UNKNOWN;
   if (mask != NULL) mask->getStorage(&mask_type);
   if (mask != NULL && mask_type == GrB_SPARSE) {
-    std::cout << "eWiseMult sparse-dense with sparse mask\n";
-    std::cout << "Error: Feature not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
+    // the result takes the mask's pattern (reference ewisemult.hpp:220-237)
+    const SparseVector<M>* ms = &mask->sparse_;
+    Index mask_nvals, nu;
+    ms->nvals(&mask_nvals);
+    u->nvals(&nu);
+    CHECK(w->allocateGpu());
+    if (mask_nvals > 0) {
+      ewiseMultSparseDenseSparseMaskKernel<<<gridFor(mask_nvals, 256), 256, 0,
+          gbStream()>>>(w->d_ind_, w->d_val_, ms->d_ind_, ms->d_val_, mask_nvals,
+          op.identity(), extractMul(op), u->d_ind_, u->d_val_, nu, v->d_val_, reverse);
+      GB_KERNEL_CHECK();
+    }
+    w->nvals_ = mask_nvals;
+    w->need_update_ = true;
+    return GrB_SUCCESS;
   }
   Index u_nvals;
   u->nvals(&u_nvals);

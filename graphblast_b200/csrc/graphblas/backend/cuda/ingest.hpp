@@ -67,7 +67,9 @@ inline void radixSortPairs(unsigned long long** keys, unsigned int** pay,
   const long long nhist = static_cast<long long>(GB_RADIX_BINS)*ntiles;
   int* hist = reinterpret_cast<int*>(gbMalloc(static_cast<size_t>(nhist)*sizeof(int)));
   const bool has_pay = (pay != NULL && *pay != NULL);
-  for (int shift = 0; shift < bits; shift += 8) {
+  for (int pos = 0; pos < bits; pos += 8) {
+    const int width = bits - pos < 8 ? bits - pos : 8;
+    const int shift = pos | (width << 8);        // see radixDigit
     radixHistogramKernel<<<ntiles, GB_RADIX_NT, 0, s>>>(hist, *keys, n, shift, ntiles);
     GB_KERNEL_CHECK();
     scanExclusiveInPlace(hist, nhist);

@@ -153,6 +153,35 @@ __global__ void ewiseMultSparseDenseKernel(Index* w_ind, W* w_val, T identity,
   }
 }
 
+// Sparse-dense eWiseMult under a SPARSE mask -> sparse output with the mask's
+// pattern (reference kernels/ewisemult.hpp:119-160): an entry is mul(u, v) where
+// the mask value is non-zero, v is not the identity and u stores that index
+// (u's indices are sorted: lower-bound search), 0 everywhere else.
+template <typename W, typename M, typename T, typename U, typename V, typename MulOp>
+__global__ void ewiseMultSparseDenseSparseMaskKernel(
+    Index* w_ind, W* w_val, const Index* mask_ind, const M* mask_val, Index mask_nvals,
+    T identity, MulOp mul_op, const Index* u_ind, const U* u_val, Index u_nvals,
+    const V* v, bool reverse) {
+  Index k = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  for (; k < mask_nvals; k += stride) {
+    const Index ind = mask_ind[k];
+    W out = static_cast<W>(0);
+    if (mask_val[k] != static_cast<M>(0)) {
+      const V b = v[ind];
+      if (b != identity) {
+        const Index at = findSorted(u_ind, 0, u_nvals, ind);
+        if (at < u_nvals && u_ind[at] == ind) {
+          const U a = u_val[at];
+          out = reverse ? mul_op(b, a) : mul_op(a, b);
+        }
+      }
+    }
+    w_ind[k] = ind;
+    w_val[k] = out;
+  }
+}
+
 // CSR values scaled by a per-row vector entry: C(i,j) = mul(A(i,j), b[i])
 // (reference eWiseMultCSRKernel, kernels/ewisemult.hpp:177-205); warp per row.
 template <typename c, typename a, typename b, typename MulOp>

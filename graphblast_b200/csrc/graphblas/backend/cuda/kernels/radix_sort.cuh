@@ -88,8 +88,13 @@ scanAddKernel(int* __restrict__ data, const int* __restrict__ tile_offset,
 #define GB_RADIX_TILE  (GB_RADIX_NT*GB_RADIX_IPT)      // 2048 keys per CTA (32 KB of static shared memory)
 #define GB_RADIX_BINS  256
 
+// `shift` carries the digit position in its low 8 bits and, above them, how many
+// bits of the digit count (the last pass of a sort over a bit count that is not a
+// multiple of 8 looks at fewer than 8).
 __device__ __forceinline__ int radixDigit(unsigned long long key, int shift) {
-  return static_cast<int>((key >> shift) & 0xffull);
+  const int pos = shift & 0xff;
+  const int width = shift >> 8;
+  return static_cast<int>((key >> pos) & ((1ull << width) - 1ull));
 }
 
 // hist[d*ntiles + tile] = #keys of the tile whose digit is d

@@ -1,19 +1,23 @@
-// graphblast_b200 backend — operation dispatch: storage-type x direction decision
-// tree behind every frontend template in graphblas/operations.hpp.
+// graphblast_b200 backend — operation dispatch: what every frontend template in
+// graphblas/operations.hpp lands on.
 //
-// Replaces reference graphblas/backend/cuda/operations.hpp:18-1435.  Template
-// parameter orders match the explicit instantiations the frontend writes
+// Stands in for reference graphblas/backend/cuda/operations.hpp:18-1435.  Template
+// parameter orders are fixed by the explicit instantiations the frontend writes
 // (backend::mxm<c,a,b,m>, vxm<W,U,a,M>, mxv<W,U,a,M>, applyVxm<W,U,a,M>;
-// reference graphblas/operations.hpp:47,85,125,863).  Operations that no
-// hot-path algorithm reaches are declared and return GrB_NOT_IMPLEMENTED
-// ("must declare").
+// reference graphblas/operations.hpp:47,85,125,863).  Structure is this
+// backend's own:
+//   * vxm and mxv share one body (mxvDispatch) — vxm is mxv on the transposed
+//     matrix, done by toggling GrB_INP1 for the duration of the call;
+//   * binary vector operations classify their operands once (pairOf) and switch
+//     on the pair instead of nesting storage tests per operation;
+//   * operations no algorithm of the path reaches are declared (the frontend
+//     must link) and answer GrB_NOT_IMPLEMENTED through one helper.
 //
 // Direction choice for vxm/mxv (reference :124-139, :252-266):
 //   CSR-only non-symmetric matrix -> vxm forced to push, mxv forced to pull;
 //   GrB_PUSHPULL  -> Vector::convert() heuristic on the input vector;
 //   GrB_PUSHONLY / GrB_PULLONLY -> input converted if needed.
-// vxm is executed as mxv on the transposed matrix by toggling GrB_INP1 for the
-// duration of the call; desc->lastmxv_ records the direction taken.
+// desc->lastmxv_ records the direction taken.
 #ifndef GRAPHBLAS_BACKEND_CUDA_OPERATIONS_HPP_
 #define GRAPHBLAS_BACKEND_CUDA_OPERATIONS_HPP_
 
@@ -30,33 +34,59 @@
 #include "graphblas/backend/cuda/assign.hpp"
 #include "graphblas/backend/cuda/reduce.hpp"
 #include "graphblas/backend/cuda/apply.hpp"
+#include "graphblas/backend/cuda/indexed.hpp"
 #include "graphblas/backend/cuda/tri.hpp"
 
 namespace graphblas {
 namespace backend {
 
+// One place that says "declared, not built" (must declare).
+inline Info notBuilt(const char* what) {
+  std::cout << "Error: " << what << " is not implemented in this backend\n";
+  return GrB_NOT_IMPLEMENTED;
+}
+
+// Storage of a pair of vector operands, classified once.
+enum OperandPair {
+  GB_PAIR_DENSE_DENSE,
+  GB_PAIR_SPARSE_DENSE,
+  GB_PAIR_DENSE_SPARSE,
+  GB_PAIR_SPARSE_SPARSE,
+  GB_PAIR_INVALID
+};
+
+inline OperandPair pairOf(Storage first, Storage second) {
+  const bool fd = first == GrB_DENSE, fs = first == GrB_SPARSE;
+  const bool sd = second == GrB_DENSE, ss = second == GrB_SPARSE;
+  if (fd && sd) return GB_PAIR_DENSE_DENSE;
+  if (fs && sd) return GB_PAIR_SPARSE_DENSE;
+  if (fd && ss) return GB_PAIR_DENSE_SPARSE;
+  if (fs && ss) return GB_PAIR_SPARSE_SPARSE;
+  return GB_PAIR_INVALID;
+}
+
+template <typename U, typename V>
+OperandPair pairOf(const Vector<U>* u, const Vector<V>* v) {
+  return pairOf(u->vec_type_, v->vec_type_);
+}
+
+// Lazily held values (dense_vector.hpp) written out for every operand given.
+template <typename X>
+Info settle(const Vector<X>* x) { return x == NULL ? GrB_SUCCESS : x->materialize(); }
+template <typename X, typename... Rest>
+Info settle(const Vector<X>* x, Rest... rest) {
+  CHECK(settle(x));
+  return settle(rest...);
+}
+
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
 Info mxm(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
     const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
-  Storage A_mat_type;
-  Storage B_mat_type;
-  CHECK(A->getStorage(&A_mat_type));
-  CHECK(B->getStorage(&B_mat_type));
-
-  if (A_mat_type == GrB_SPARSE && B_mat_type == GrB_SPARSE) {
-    CHECK(C->setStorage(GrB_SPARSE));
-    if (mask) {
-      CHECK(spgemmMasked(&C->sparse_, mask, accum, op, &A->sparse_, &B->sparse_, desc));
-    } else {
-      std::cout << "Error: Unmasked SpGEMM not implemented yet!\n";
-      return GrB_NOT_IMPLEMENTED;
-    }
-  } else {
-    std::cout << "Error: SpMM and GEMM not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  }
-  return GrB_SUCCESS;
+  if (!A->isSparse() || !B->isSparse()) return notBuilt("mxm with a dense operand (SpMM / GEMM)");
+  if (mask == NULL) return notBuilt("unmasked SpGEMM");
+  CHECK(C->setStorage(GrB_SPARSE));
+  return spgemmMasked(&C->sparse_, mask, accum, op, &A->sparse_, &B->sparse_, desc);
 }
 
 // Shared body of vxm / mxv once the descriptor says which side is transposed.
@@ -194,66 +224,44 @@ Info mxv(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
   return GrB_SUCCESS;
 }
 
+// w = u .* v.  Results: dense x dense -> dense (sparse when the mask is sparse),
+// anything with a sparse operand -> sparse; sparse x sparse reads v as dense, as
+// the reference does by flipping its tag (operations.hpp:365-371).
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
 Info eWiseMult(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
     const Vector<U>* u, const Vector<V>* v, Descriptor* desc) {
-  Vector<V>* v_t = const_cast<Vector<V>*>(v);
-  CHECK(u->materialize());
-  CHECK(v->materialize());
-  CHECK(w->materialize());
-  if (mask != NULL) CHECK(mask->materialize());
-
-  Storage u_vec_type;
-  Storage v_vec_type;
-  CHECK(u->getStorage(&u_vec_type));
-  CHECK(v->getStorage(&v_vec_type));
-
-  // sparse x sparse: the reference flips v's tag to dense (operations.hpp:365-371)
-  if (u_vec_type == GrB_SPARSE && v_vec_type == GrB_SPARSE)
-    CHECK(v_t->setStorage(GrB_DENSE));
-  CHECK(u->getStorage(&u_vec_type));
-  CHECK(v->getStorage(&v_vec_type));
-
-  if (u_vec_type == GrB_DENSE && v_vec_type == GrB_DENSE) {
-    if (mask != NULL) {
-      Storage mask_type;
-      CHECK(mask->getStorage(&mask_type));
-      if (mask_type == GrB_DENSE) {
-        CHECK(w->setStorage(GrB_DENSE));
-        CHECK(eWiseMultInner(&w->dense_, mask, accum, op,
-            &u->dense_, &v->dense_, desc));
-      } else if (mask_type == GrB_SPARSE) {
+  CHECK(settle(u, v, w, mask));
+  if (pairOf(u, v) == GB_PAIR_SPARSE_SPARSE)
+    CHECK(const_cast<Vector<V>*>(v)->setStorage(GrB_DENSE));
+  switch (pairOf(u, v)) {
+    case GB_PAIR_DENSE_DENSE:
+      if (mask != NULL && mask->vec_type_ == GrB_SPARSE) {
         CHECK(w->setStorage(GrB_SPARSE));
-        CHECK(eWiseMultInner(&w->sparse_,
-            &mask->sparse_, accum, op, &u->dense_, &v->dense_, desc));
-      } else {
-        return GrB_INVALID_OBJECT;
+        return eWiseMultInner(&w->sparse_, &mask->sparse_, accum, op, &u->dense_,
+            &v->dense_, desc);
       }
-    } else {
+      if (mask != NULL && mask->vec_type_ != GrB_DENSE) return GrB_INVALID_OBJECT;
       CHECK(w->setStorage(GrB_DENSE));
-      CHECK(eWiseMultInner(&w->dense_, mask, accum, op, &u->dense_, &v->dense_, desc));
-    }
-  } else if (u_vec_type == GrB_SPARSE && v_vec_type == GrB_DENSE) {
-    CHECK(w->setStorage(GrB_SPARSE));
-    CHECK(eWiseMultInner(&w->sparse_, mask, accum, op,
-        &u->sparse_, &v->dense_, false, desc));
-  } else if (u_vec_type == GrB_DENSE && v_vec_type == GrB_SPARSE) {
-    CHECK(w->setStorage(GrB_SPARSE));
-    CHECK(eWiseMultInner(&w->sparse_, mask, accum, op,
-        &v->sparse_, &u->dense_, true, desc));
-  } else {
-    return GrB_INVALID_OBJECT;
+      return eWiseMultInner(&w->dense_, mask, accum, op, &u->dense_, &v->dense_, desc);
+    case GB_PAIR_SPARSE_DENSE:
+      CHECK(w->setStorage(GrB_SPARSE));
+      return eWiseMultInner(&w->sparse_, mask, accum, op, &u->sparse_, &v->dense_,
+          false, desc);
+    case GB_PAIR_DENSE_SPARSE:          // operands swapped, the kernel is told
+      CHECK(w->setStorage(GrB_SPARSE));
+      return eWiseMultInner(&w->sparse_, mask, accum, op, &v->sparse_, &u->dense_,
+          true, desc);
+    default:
+      return GrB_INVALID_OBJECT;
   }
-  return GrB_SUCCESS;
 }
 
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
 Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
     const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
-  std::cout << "Error: eWiseMult matrix variant not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("eWiseMult of two matrices");
 }
 
 // Extension: matrix (x) broadcast scalar
@@ -261,21 +269,11 @@ template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
 Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
     const Matrix<a>* A, b val, Descriptor* desc) {
-  Storage A_mat_type;
-  CHECK(A->getStorage(&A_mat_type));
-  if (A_mat_type != GrB_SPARSE) {
-    std::cout << "eWiseMult Dense Matrix Broadcast Scalar\n";
-    std::cout << "Error: Feature not implemented yet!\n";
-    return (A_mat_type == GrB_DENSE) ? GrB_NOT_IMPLEMENTED : GrB_INVALID_OBJECT;
-  }
-  if (mask != NULL) {
-    std::cout << "eWiseMult Sparse Matrix Broadcast Scalar with Mask\n";
-    std::cout << "Error: Feature not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  }
+  if (A->isDense()) return notBuilt("eWiseMult of a dense matrix and a scalar");
+  if (!A->isSparse()) return GrB_INVALID_OBJECT;
+  if (mask != NULL) return notBuilt("masked eWiseMult of a matrix and a scalar");
   CHECK(C->setStorage(GrB_SPARSE));
-  CHECK(eWiseMultInner(&C->sparse_, mask, accum, op, &A->sparse_, val, desc));
-  return GrB_SUCCESS;
+  return eWiseMultInner(&C->sparse_, mask, accum, op, &A->sparse_, val, desc);
 }
 
 // Extension: matrix (x) broadcast vector (column vector; row vector when
@@ -288,89 +286,54 @@ Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT o
   CHECK(desc->get(GrB_INP0, &inp0_mode));
   CHECK(desc->get(GrB_INP1, &inp1_mode));
   if (inp0_mode != GrB_DEFAULT) return GrB_INVALID_VALUE;
-  CHECK(B->materialize());
-
-  Storage A_mat_type;
-  Storage B_vec_type;
-  CHECK(A->getStorage(&A_mat_type));
-  CHECK(B->getStorage(&B_vec_type));
-
-  if (A_mat_type != GrB_SPARSE) {
-    std::cout << "eWiseMult Dense Matrix Broadcast Vector\n";
-    std::cout << "Error: Feature not implemented yet!\n";
-    return (A_mat_type == GrB_DENSE) ? GrB_NOT_IMPLEMENTED : GrB_INVALID_OBJECT;
-  }
-  if (mask != NULL) {
-    std::cout << "eWiseMult Sparse Matrix Broadcast Vector with Mask\n";
-    std::cout << "Error: Feature not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  }
+  CHECK(settle(B));
+  if (A->isDense()) return notBuilt("eWiseMult of a dense matrix and a vector");
+  if (!A->isSparse()) return GrB_INVALID_OBJECT;
+  if (mask != NULL) return notBuilt("masked eWiseMult of a matrix and a vector");
   CHECK(C->setStorage(GrB_SPARSE));
-  if (B_vec_type == GrB_SPARSE) {
-    std::cout << "eWiseMult Sparse Matrix Broadcast Sparse Vector\n";
-    std::cout << "Error: Feature not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  }
-  if (inp1_mode != GrB_TRAN)
-    CHECK(eWiseMultColInner(&C->sparse_, mask, accum, op,
-        &A->sparse_, &B->dense_, desc));
-  else
-    CHECK(eWiseMultRowInner(&C->sparse_, mask, accum, op,
-        &A->sparse_, &B->dense_, desc));
-  return GrB_SUCCESS;
+  if (B->vec_type_ == GrB_SPARSE)
+    return notBuilt("eWiseMult of a matrix and a sparse vector");
+  if (inp1_mode == GrB_TRAN)
+    return eWiseMultRowInner(&C->sparse_, mask, accum, op, &A->sparse_, &B->dense_, desc);
+  return eWiseMultColInner(&C->sparse_, mask, accum, op, &A->sparse_, &B->dense_, desc);
 }
 
+// w = u + v, always dense.  A sparse operand that is also the output is
+// densified first (reference :598-607).
 template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
 Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
     const Vector<U>* u, const Vector<V>* v, Descriptor* desc) {
-  Vector<U>* u_t = const_cast<Vector<U>*>(u);
-  Vector<V>* v_t = const_cast<Vector<V>*>(v);
-  CHECK(u->materialize());
-  CHECK(v->materialize());
-  CHECK(w->materialize());
-  if (mask != NULL) CHECK(mask->materialize());
-
-  Storage u_vec_type;
-  Storage v_vec_type;
-  CHECK(u->getStorage(&u_vec_type));
-  CHECK(v->getStorage(&v_vec_type));
-
-  // An in-place sparse operand is densified first (reference :598-607).
-  const void* w_addr = reinterpret_cast<const void*>(w);
-  if (reinterpret_cast<const void*>(u) == w_addr && u_vec_type == GrB_SPARSE) {
-    u_t->sparse2dense(op.identity(), desc);
-    u_vec_type = GrB_DENSE;
-  } else if (reinterpret_cast<const void*>(v) == w_addr &&
-             v_vec_type == GrB_SPARSE) {
-    v_t->sparse2dense(op.identity(), desc);
-    v_vec_type = GrB_DENSE;
-  }
-
+  CHECK(settle(u, v, w, mask));
+  const void* out = reinterpret_cast<const void*>(w);
+  if (reinterpret_cast<const void*>(u) == out && u->vec_type_ == GrB_SPARSE)
+    const_cast<Vector<U>*>(u)->sparse2dense(op.identity(), desc);
+  else if (reinterpret_cast<const void*>(v) == out && v->vec_type_ == GrB_SPARSE)
+    const_cast<Vector<V>*>(v)->sparse2dense(op.identity(), desc);
+  const OperandPair pair = pairOf(u, v);
   CHECK(w->setStorage(GrB_DENSE));
-  if (u_vec_type == GrB_SPARSE && v_vec_type == GrB_SPARSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_, &v->sparse_, desc));
-  } else if (u_vec_type == GrB_DENSE && v_vec_type == GrB_DENSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->dense_, &v->dense_, desc));
-  } else if (u_vec_type == GrB_SPARSE && v_vec_type == GrB_DENSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op,
-        &u->sparse_, &v->dense_, false, desc));
-  } else if (u_vec_type == GrB_DENSE && v_vec_type == GrB_SPARSE) {
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op,
-        &v->sparse_, &u->dense_, true, desc));
-  } else {
-    std::cout << "Error: eWiseAdd backend invalid choice!\n";
-    return GrB_INVALID_OBJECT;
+  switch (pair) {
+    case GB_PAIR_DENSE_DENSE:
+      return eWiseAddInner(&w->dense_, mask, accum, op, &u->dense_, &v->dense_, desc);
+    case GB_PAIR_SPARSE_SPARSE:
+      return eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_, &v->sparse_, desc);
+    case GB_PAIR_SPARSE_DENSE:
+      return eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_, &v->dense_,
+          false, desc);
+    case GB_PAIR_DENSE_SPARSE:          // operands swapped, the kernel is told
+      return eWiseAddInner(&w->dense_, mask, accum, op, &v->sparse_, &u->dense_,
+          true, desc);
+    default:
+      std::cout << "Error: eWiseAdd backend invalid choice!\n";
+      return GrB_INVALID_OBJECT;
   }
-  return GrB_SUCCESS;
 }
 
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
 Info eWiseAdd(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
     const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
-  std::cout << "Error: eWiseAdd matrix variant not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("eWiseAdd of two matrices");
 }
 
 // Extension: vector (+) broadcast scalar
@@ -378,65 +341,45 @@ template <typename W, typename U, typename V, typename M,
           typename BinaryOpT,     typename SemiringT>
 Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
     const Vector<U>* u, V val, Descriptor* desc) {
-  CHECK(u->materialize());
-  CHECK(w->materialize());
-  Storage u_vec_type;
-  CHECK(u->getStorage(&u_vec_type));
-  if (u_vec_type != GrB_DENSE && u_vec_type != GrB_SPARSE)
-    return GrB_INVALID_OBJECT;
-  if (mask != NULL) {
-    std::cout << "eWiseAdd Vector-Scalar with Mask\n";
-    std::cout << "Error: Feature not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  }
+  CHECK(settle(u, w));
+  const Storage u_type = u->vec_type_;
+  if (u_type != GrB_DENSE && u_type != GrB_SPARSE) return GrB_INVALID_OBJECT;
+  if (mask != NULL) return notBuilt("masked eWiseAdd of a vector and a scalar");
   CHECK(w->setStorage(GrB_DENSE));
-  if (u_vec_type == GrB_DENSE)
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->dense_, val, desc));
-  else
-    CHECK(eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_, val, desc));
-  return GrB_SUCCESS;
+  if (u_type == GrB_DENSE)
+    return eWiseAddInner(&w->dense_, mask, accum, op, &u->dense_, val, desc);
+  return eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_, val, desc);
 }
 
 template <typename W, typename U, typename M,
           typename BinaryOpT>
 Info extract(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, const Vector<U>* u,
     const std::vector<Index>* indices, Index nindices, Descriptor* desc) {
-  std::cout << "Error: extract vector variant not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("extract of a vector");
 }
 
 template <typename W, typename U, typename M,
           typename BinaryOpT>
 Info assignIndexed(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
     const Vector<U>* u, int* indices, Index nindices, Descriptor* desc) {
-  std::cout << "Error: assignIndexed not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("assignIndexed");
 }
 
-// Masked constant assign
+// Masked constant assign.  The target is written in part, so its lazily held
+// values are written out first; a dense mask is read through its bitmap shadow
+// when that is current, except by the sparse-target filter, which reads values.
 template <typename W, typename T, typename M,
           typename BinaryOpT>
 Info assign(Vector<W>* w, Vector<M>* mask, BinaryOpT accum, T val,
     const Vector<Index>* indices, Index nindices, Descriptor* desc) {
-  if (desc->debug()) {
-    std::cout << "===Begin assign===\n";
-    std::cout << "Input: " << val << std::endl;
-  }
-
-  Storage vec_type;
-  CHECK(w->getStorage(&vec_type));
-  // The target is written in part; a dense mask is read through its bitmap
-  // shadow when that is current (which lazily held values imply), except by the
-  // sparse-target filter, which reads mask values.
-  CHECK(w->materialize());
-  if (vec_type == GrB_SPARSE && mask != NULL) CHECK(mask->materialize());
-
-  if (vec_type == GrB_SPARSE) {
+  if (desc->debug()) std::cout << "===Begin assign===\nInput: " << val << std::endl;
+  CHECK(settle(w));
+  if (w->vec_type_ == GrB_SPARSE) {
+    CHECK(settle(mask));
     CHECK(assignSparse(&w->sparse_, mask, accum, val, indices, nindices, desc));
-  } else if (vec_type == GrB_DENSE) {
+  } else if (w->vec_type_ == GrB_DENSE) {
     CHECK(assignDense(&w->dense_, mask, accum, val, indices, nindices, desc));
   }
-
   if (desc->debug()) {
     std::cout << "===End assign===\n";
     CHECK(w->print());
@@ -448,41 +391,33 @@ template <typename W, typename U, typename M,
           typename BinaryOpT,     typename UnaryOpT>
 Info apply(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, UnaryOpT op,
     const Vector<U>* u, Descriptor* desc) {
-  Vector<U>* u_t = const_cast<Vector<U>*>(u);
-  CHECK(u->materialize());
-  CHECK(w->materialize());
-  if (mask != NULL) CHECK(mask->materialize());
-  Storage u_vec_type;
-  CHECK(u->getStorage(&u_vec_type));
-  if (u_vec_type == GrB_SPARSE) {
+  Vector<U>* source = const_cast<Vector<U>*>(u);
+  CHECK(settle(u, w, mask));
+  if (u->vec_type_ == GrB_SPARSE) {
     CHECK(w->setStorage(GrB_SPARSE));
-    applySparse(&w->sparse_, mask, accum, op, &u_t->sparse_, desc);
-  } else if (u_vec_type == GrB_DENSE) {
-    CHECK(w->setStorage(GrB_DENSE));
-    applyDense(&w->dense_, mask, accum, op, &u_t->dense_, desc);
-  } else {
-    return GrB_UNINITIALIZED_OBJECT;
+    return applySparse(&w->sparse_, mask, accum, op, &source->sparse_, desc);
   }
-  return GrB_SUCCESS;
+  if (u->vec_type_ == GrB_DENSE) {
+    CHECK(w->setStorage(GrB_DENSE));
+    return applyDense(&w->dense_, mask, accum, op, &source->dense_, desc);
+  }
+  return GrB_UNINITIALIZED_OBJECT;
 }
 
 template <typename c, typename a, typename m,
           typename BinaryOpT,     typename UnaryOpT>
 Info apply(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, UnaryOpT op,
     const Matrix<a>* A, Descriptor* desc) {
-  Matrix<a>* A_t = const_cast<Matrix<a>*>(A);
-  Storage A_mat_type;
-  CHECK(A->getStorage(&A_mat_type));
-  if (A_mat_type == GrB_SPARSE) {
+  Matrix<a>* source = const_cast<Matrix<a>*>(A);
+  if (A->isSparse()) {
     CHECK(C->setStorage(GrB_SPARSE));
-    applySparse(&C->sparse_, mask, accum, op, &A_t->sparse_, desc);
-  } else if (A_mat_type == GrB_DENSE) {
-    CHECK(C->setStorage(GrB_DENSE));
-    applyDense(&C->dense_, mask, accum, op, &A_t->dense_, desc);
-  } else {
-    return GrB_UNINITIALIZED_OBJECT;
+    return applySparse(&C->sparse_, mask, accum, op, &source->sparse_, desc);
   }
-  return GrB_SUCCESS;
+  if (A->isDense()) {
+    CHECK(C->setStorage(GrB_DENSE));
+    return applyDense(&C->dense_, mask, accum, op, &source->dense_, desc);
+  }
+  return GrB_UNINITIALIZED_OBJECT;
 }
 
 // matrix rows -> vector
@@ -490,39 +425,21 @@ template <typename W, typename a, typename M,
           typename BinaryOpT,     typename MonoidT>
 Info reduce(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
     const Matrix<a>* A, Descriptor* desc) {
-  Storage mat_type;
-  CHECK(A->getStorage(&mat_type));
   CHECK(w->setStorage(GrB_DENSE));
-
-  if (mask != NULL) {
-    std::cout << "Error: Masked reduce not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  }
-  if (mat_type == GrB_SPARSE)
-    CHECK(reduceInner(&w->dense_, mask, accum, op, &A->sparse_, desc));
-  else if (mat_type == GrB_DENSE)
-    CHECK(reduceInner(&w->dense_, mask, accum, op, &A->dense_, desc));
-  else
-    return GrB_UNINITIALIZED_OBJECT;
-  return GrB_SUCCESS;
+  if (mask != NULL) return notBuilt("masked reduce");
+  if (A->isSparse()) return reduceInner(&w->dense_, mask, accum, op, &A->sparse_, desc);
+  if (A->isDense())  return reduceInner(&w->dense_, mask, accum, op, &A->dense_, desc);
+  return GrB_UNINITIALIZED_OBJECT;
 }
 
 // vector -> scalar
 template <typename T, typename U,
           typename BinaryOpT, typename MonoidT>
 Info reduce(T* val, BinaryOpT accum, MonoidT op, const Vector<U>* u, Descriptor* desc) {
-  Storage vec_type;
-  CHECK(u->getStorage(&vec_type));
-
-  if (vec_type == GrB_SPARSE)
-    CHECK(reduceInner(val, accum, op, &u->sparse_, desc));
-  else if (vec_type == GrB_DENSE)
-    CHECK(reduceInner(val, accum, op, &u->dense_, desc));
-  else
-    return GrB_UNINITIALIZED_OBJECT;
-
-  if (desc->debug())
-    std::cout << "reduce output: " << *val << std::endl;
+  if (u->vec_type_ == GrB_SPARSE)     CHECK(reduceInner(val, accum, op, &u->sparse_, desc));
+  else if (u->vec_type_ == GrB_DENSE) CHECK(reduceInner(val, accum, op, &u->dense_, desc));
+  else return GrB_UNINITIALIZED_OBJECT;
+  if (desc->debug()) std::cout << "reduce output: " << *val << std::endl;
   return GrB_SUCCESS;
 }
 
@@ -530,92 +447,65 @@ Info reduce(T* val, BinaryOpT accum, MonoidT op, const Vector<U>* u, Descriptor*
 template <typename T, typename a,
           typename BinaryOpT,     typename MonoidT>
 Info reduce(T* val, BinaryOpT accum, MonoidT op, const Matrix<a>* A, Descriptor* desc) {
-  Storage mat_type;
-  CHECK(A->getStorage(&mat_type));
-
-  if (mat_type == GrB_SPARSE) {
-    CHECK(reduceInner(val, accum, op, &A->sparse_, desc));
-  } else if (mat_type == GrB_DENSE) {
-    std::cout << "Error: reduce matrix-scalar for dense matrix\n";
-    std::cout << "not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  } else {
-    return GrB_UNINITIALIZED_OBJECT;
-  }
-  return GrB_SUCCESS;
+  if (A->isSparse()) return reduceInner(val, accum, op, &A->sparse_, desc);
+  if (A->isDense())  return notBuilt("reduce of a dense matrix to a scalar");
+  return GrB_UNINITIALIZED_OBJECT;
 }
 
 template <typename c, typename a, typename m,
           typename BinaryOpT>
 Info transpose(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, const Matrix<a>* A,
     Descriptor* desc) {
-  std::cout << "Error: transpose not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("transpose");
 }
-
-// ---- Declared-only operations (not reached by bfs/sssp/pr/tc) -------------
 
 template <typename T, typename a, typename b,
           typename SemiringT>
 Info traceMxmTranspose(T* val, SemiringT op, const Matrix<a>* A, const Matrix<b>* B,
     Descriptor* desc) {
-  std::cout << "Error: Trace operator not implemented!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("traceMxmTranspose");
 }
+
+// ---- index-driven vector operations (indexed.hpp) ------------------------------
 
 template <typename W, typename M, typename U, typename T>
 Info scatter(Vector<W>* w, const Vector<M>* mask, const Vector<U>* u, T val,
     Descriptor* desc) {
-  std::cout << "Error: scatter not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return scatterConstant(w, mask, u, val, desc);
 }
 
 template <typename W, typename U, typename M, typename I,
           typename BinaryOpT>
 Info assignScatter(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
     const Vector<U>* u, const Vector<I>* indices, Descriptor* desc) {
-  std::cout << "Error: assignScatter not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return indexedMove<false>(w, mask, u, indices, desc);
 }
 
 template <typename W, typename U, typename M, typename I,
           typename BinaryOpT>
 Info extractGather(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
     const Vector<U>* u, const Vector<I>* indices, Descriptor* desc) {
-  std::cout << "Error: extractGather not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return indexedMove<true>(w, mask, u, indices, desc);
 }
 
 template <typename W, typename a>
 Info graphColor(Vector<W>* w, const Matrix<a>* A, Descriptor* desc) {
-  std::cout << "Error: graphColor (cuSPARSE csrcolor) not implemented!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("graphColor (cuSPARSE csrcolor, gone from CUDA 12)");
 }
 
 template <typename W, typename U, typename a, typename M,
           typename BinaryOpT, typename SemiringT>
 Info applyVxm(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
     const Vector<U>* u, const Matrix<a>* A, Descriptor* desc) {
-  std::cout << "Error: applyVxm not implemented yet!\n";
-  return GrB_NOT_IMPLEMENTED;
+  return notBuilt("applyVxm");
 }
 
 template <typename c, typename a>
 Info tril(Matrix<c>* C, Matrix<a>* A, Descriptor* desc) {
-  Storage A_mat_type;
-  CHECK(A->getStorage(&A_mat_type));
-
-  if (reinterpret_cast<void*>(C) != reinterpret_cast<void*>(A))
-    CHECK(C->dup(A));
-
-  if (A_mat_type == GrB_SPARSE) {
-    CHECK(C->setStorage(GrB_SPARSE));
-    CHECK(trilSparse(&C->sparse_, &A->sparse_, desc));
-  } else {
-    std::cout << "Error: tril for dense matrix not implemented yet!\n";
-    return GrB_NOT_IMPLEMENTED;
-  }
-  return GrB_SUCCESS;
+  if (reinterpret_cast<void*>(C) != reinterpret_cast<void*>(A)) CHECK(C->dup(A));
+  if (!A->isSparse()) return notBuilt("tril of a dense matrix");
+  CHECK(C->setStorage(GrB_SPARSE));
+  return trilSparse(&C->sparse_, &A->sparse_, desc);
 }
 }  // namespace backend
 }  // namespace graphblas

@@ -1,12 +1,16 @@
 // graphblast_b200 backend — Vector<T>: dual-storage (sparse list / dense array)
 // vector whose storage follows the traversal direction.
 //
-// Replaces reference graphblas/backend/cuda/vector.hpp:27-454.  The direction
-// heuristic in convert() is the reference's (vector.hpp:292-323): with
-// ratio = nnz/size, sparse->dense when ratio > switchpoint and growing,
-// dense->sparse when ratio <= switchpoint and shrinking, otherwise remember ratio_.
-// Conversions run as device kernels: sparse->dense = fill + scatter,
-// dense->sparse = ordered compaction (kernels/compact.cuh).
+// Stands in for reference graphblas/backend/cuda/vector.hpp:27-454: same method
+// set (the frontend forwards to it) and the members tests reach (sparse_, dense_,
+// vec_type_).  Everything that merely hands a call to whichever storage is active
+// goes through ONE helper (onActive) that visits the active storage with a generic
+// callable; what is specific to this class is the storage state machine:
+// the direction heuristic of convert() — the reference's (vector.hpp:292-323):
+// with ratio = nnz/size, sparse->dense when ratio > switchpoint and growing,
+// dense->sparse when ratio <= switchpoint and shrinking, otherwise remember ratio_ —
+// and the conversions, which run as device kernels: sparse->dense = fill +
+// scatter, dense->sparse = ordered compaction (kernels/compact.cuh).
 #ifndef GRAPHBLAS_BACKEND_CUDA_VECTOR_HPP_
 #define GRAPHBLAS_BACKEND_CUDA_VECTOR_HPP_
 
@@ -27,45 +31,112 @@ namespace backend {
 template <typename T>
 class Vector {
  public:
-  Vector()
-      : nsize_(0), nvals_(0), sparse_(0), dense_(0), vec_type_(GrB_UNKNOWN),
-        ratio_(0) {}
+  Vector() : nsize_(0), nvals_(0), sparse_(0), dense_(0), vec_type_(GrB_UNKNOWN), ratio_(0) {}
   explicit Vector(Index nsize)
       : nsize_(nsize), nvals_(0), sparse_(nsize), dense_(nsize),
         vec_type_(GrB_UNKNOWN), ratio_(0) {}
-
   ~Vector() {}
 
-  // C API Methods
-  Info nnew(Index nsize_t);
-  Info dup(const Vector* rhs);
-  Info clear();
-  Info size(Index* nsize_t);
-  Info nvals(Index* nvals_t);
-  template <typename BinaryOpT>
-  Info build(const std::vector<Index>* indices, const std::vector<T>* values,
-      Index nvals, BinaryOpT dup);
-  Info build(const std::vector<T>* values, Index nvals);
-  Info build(Index* indices, T* values, Index nvals);
-  Info build(T* values, Index nvals);
-  Info setElement(T val, Index index);
-  Info extractElement(T* val, Index index);
-  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n);
-  Info extractTuples(std::vector<T>* values, Index* n);
-
-  // handy methods
-  const T& operator[](Index ind);
-  Info resize(Index nvals);
-  Info fill(T val);
-  Info fillAscending(Index nvals);
-  Info print(bool force_update = false);
-  Info countUnique(Index* count);
-  inline Info setStorage(Storage  vec_type);
-  inline Info getStorage(Storage* vec_type) const;
+  // ---- storage state ---------------------------------------------------------
+  Info setStorage(Storage vec_type) {
+    vec_type_ = vec_type;
+    return onActive([](auto& active) { return active.allocateGpu(); }, GrB_SUCCESS);
+  }
+  Info getStorage(Storage* vec_type) const { *vec_type = vec_type_; return GrB_SUCCESS; }
   Info convert(T identity, float switchpoint, Descriptor* desc);
   Info sparse2dense(T identity, Descriptor* desc = NULL);
   Info dense2sparse(T identity, Descriptor* desc);
   Info swap(Vector* rhs);
+  // Writes out lazily held values of a dense vector (dense_vector.hpp).
+  Info materialize() { return vec_type_ == GrB_DENSE ? dense_.materialize() : GrB_SUCCESS; }
+  Info materialize() const { return const_cast<Vector*>(this)->materialize(); }
+
+  // ---- construction: the call decides the storage (fill / dense values -> dense,
+  // index-value lists -> sparse; reference :150-156, 241-245) --------------------
+  Info nnew(Index nsize) {
+    nsize_ = nsize;
+    CHECK(sparse_.nnew(nsize));
+    return dense_.nnew(nsize);
+  }
+  template <typename BinaryOpT>
+  Info build(const std::vector<Index>* indices, const std::vector<T>* values,
+      Index nvals, BinaryOpT dup) {
+    vec_type_ = GrB_SPARSE;
+    return sparse_.build(indices, values, nvals, dup);
+  }
+  Info build(const std::vector<T>* values, Index nvals) {
+    vec_type_ = GrB_DENSE;
+    return dense_.build(values, nvals);
+  }
+  Info build(Index* indices, T* values, Index nvals) {
+    vec_type_ = GrB_SPARSE;
+    return sparse_.build(indices, values, nvals);
+  }
+  Info build(T* values, Index nvals) {
+    vec_type_ = GrB_DENSE;
+    return dense_.build(values, nvals);
+  }
+  Info fill(T val) {
+    if (vec_type_ != GrB_DENSE) CHECK(setStorage(GrB_DENSE));
+    return dense_.fill(val);
+  }
+  Info fillAscending(Index nvals) {
+    if (vec_type_ != GrB_DENSE) CHECK(setStorage(GrB_DENSE));
+    return dense_.fillAscending(nvals);
+  }
+  Info dup(const Vector* rhs) {
+    vec_type_ = rhs->vec_type_;
+    if (vec_type_ == GrB_SPARSE) return sparse_.dup(&rhs->sparse_);
+    if (vec_type_ == GrB_DENSE)  return dense_.dup(&rhs->dense_);
+    std::cout << "Error: dup of a vector without storage\n";
+    return GrB_UNINITIALIZED_OBJECT;
+  }
+  // Storage becomes unknown; the dense side is not zero-filled here (the
+  // reference does), the fill happens when a storage is chosen again.
+  Info clear() {
+    vec_type_ = GrB_UNKNOWN;
+    nvals_ = 0;
+    return sparse_.clear();
+  }
+
+  // ---- calls handed to the active storage ----------------------------------------
+  Info size(Index* out) {
+    return onActive([&](auto& active) { return active.size(&nsize_); }, GrB_SUCCESS,
+                    [&] { *out = nsize_; });
+  }
+  Info nvals(Index* out) {
+    return onActive([&](auto& active) { return active.nvals(&nvals_); }, GrB_SUCCESS,
+                    [&] { *out = nvals_; });
+  }
+  Info setElement(T val, Index index) {
+    return onActive([&](auto& active) { return active.setElement(val, index); });
+  }
+  Info extractElement(T* val, Index index) {
+    return onActive([&](auto& active) { return active.extractElement(val, index); });
+  }
+  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n) {
+    return onActive([&](auto& active) { return active.extractTuples(indices, values, n); });
+  }
+  // Values only: a sparse vector is densified with fill value 0 first
+  // (reference :208-217).
+  Info extractTuples(std::vector<T>* values, Index* n) {
+    if (vec_type_ == GrB_SPARSE) CHECK(sparse2dense(static_cast<T>(0)));
+    if (vec_type_ != GrB_DENSE) return GrB_UNINITIALIZED_OBJECT;
+    return dense_.extractTuples(values, n);
+  }
+  Info resize(Index nvals) {
+    return onActive([&](auto& active) { return active.resize(nvals); });
+  }
+  Info print(bool force_update = false) {
+    return onActive([&](auto& active) { return active.print(force_update); }, GrB_SUCCESS);
+  }
+  Info countUnique(Index* count) { return GrB_SUCCESS; }
+  const T& operator[](Index ind) {
+    static T none = T();
+    if (vec_type_ == GrB_SPARSE) return sparse_[ind];
+    if (vec_type_ == GrB_DENSE)  return dense_[ind];
+    return none;
+  }
 
  public:  // (private in the reference; its drivers `#define private public`)
   Index           nsize_;
@@ -73,16 +144,23 @@ class Vector {
   SparseVector<T> sparse_;
   DenseVector<T>  dense_;
   Storage         vec_type_;
-
   float           ratio_;  // nnz/size seen at the previous convert()
 
-  // Writes out lazily held values of a dense vector (dense_vector.hpp).
-  Info materialize() {
-    if (vec_type_ == GrB_DENSE) return dense_.materialize();
-    return GrB_SUCCESS;
+ private:
+  // Visits the active storage; `otherwise` is the answer when there is none.
+  // `then` runs after a successful visit (or when there is no storage and
+  // `otherwise` is success).
+  template <typename Visit>
+  Info onActive(Visit visit, Info otherwise = GrB_UNINITIALIZED_OBJECT) {
+    return onActive(visit, otherwise, [] {});
   }
-  Info materialize() const {
-    return const_cast<Vector*>(this)->materialize();
+  template <typename Visit, typename Then>
+  Info onActive(Visit visit, Info otherwise, Then then) {
+    Info status = otherwise;
+    if (vec_type_ == GrB_SPARSE)     status = visit(sparse_);
+    else if (vec_type_ == GrB_DENSE) status = visit(dense_);
+    if (status == GrB_SUCCESS) then();
+    return status;
   }
 };
 
@@ -227,188 +305,17 @@ Info Vector<T>::dense2sparse(T identity, Descriptor* desc) {
 
 template <typename T>
 Info Vector<T>::swap(Vector* rhs) {  // NOLINT(build/include_what_you_use)
+  // only vectors in the same, known storage can trade contents (reference :430-434)
   if (vec_type_ != rhs->vec_type_ || vec_type_ == GrB_UNKNOWN)
     return GrB_INVALID_OBJECT;
-
-  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.swap(&rhs->sparse_));
-  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.swap(&rhs->dense_));
-
+  if (vec_type_ == GrB_SPARSE) CHECK(sparse_.swap(&rhs->sparse_));
+  else                         CHECK(dense_.swap(&rhs->dense_));
   std::swap(nsize_, rhs->nsize_);
   std::swap(nvals_, rhs->nvals_);
   std::swap(ratio_, rhs->ratio_);
   return GrB_SUCCESS;
 }
 
-template <typename T>
-inline Info Vector<T>::setStorage(Storage vec_type) {
-  vec_type_ = vec_type;
-  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.allocateGpu());
-  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.allocateGpu());
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-inline Info Vector<T>::getStorage(Storage* vec_type) const {
-  *vec_type = vec_type_;
-  return GrB_SUCCESS;
-}
-
-// ---- construction, element access and forwarding to the active storage ----
-
-template <typename T>
-Info Vector<T>::nnew(Index nsize_t) {
-  nsize_ = nsize_t;
-  CHECK(sparse_.nnew(nsize_t));
-  CHECK(dense_.nnew(nsize_t));
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-Info Vector<T>::dup(const Vector* rhs) {
-  vec_type_ = rhs->vec_type_;
-  if (vec_type_ == GrB_SPARSE)
-    return sparse_.dup(&rhs->sparse_);
-  else if (vec_type_ == GrB_DENSE)
-    return dense_.dup(&rhs->dense_);
-  std::cout << "Error: Failed to call dup!\n";
-  return GrB_UNINITIALIZED_OBJECT;
-}
-
-template <typename T>
-Info Vector<T>::clear() {
-  vec_type_ = GrB_UNKNOWN;
-  nvals_    = 0;
-  CHECK(sparse_.clear());
-  // dense_.clear() zero-fills in the reference; storage is unknown after
-  // clear(), so the fill is deferred until a storage is chosen.
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-Info Vector<T>::size(Index* nsize_t) {
-  Index nsize;
-  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.size(&nsize));
-  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.size(&nsize));
-  else                              nsize = nsize_;
-  nsize_   = nsize;
-  *nsize_t = nsize;
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-Info Vector<T>::nvals(Index* nvals_t) {
-  Index new_nvals;
-  if (vec_type_ == GrB_SPARSE)      CHECK(sparse_.nvals(&new_nvals));
-  else if (vec_type_ == GrB_DENSE)  CHECK(dense_.nvals(&new_nvals));
-  else                              new_nvals = nvals_;
-  nvals_   = new_nvals;
-  *nvals_t = new_nvals;
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-template <typename BinaryOpT>
-Info Vector<T>::build(const std::vector<Index>* indices, const std::vector<T>* values,
-    Index nvals, BinaryOpT dup) {
-  vec_type_ = GrB_SPARSE;
-  return sparse_.build(indices, values, nvals, dup);
-}
-
-template <typename T>
-Info Vector<T>::build(const std::vector<T>* values, Index nvals) {
-  vec_type_ = GrB_DENSE;
-  return dense_.build(values, nvals);
-}
-
-template <typename T>
-Info Vector<T>::build(Index* indices, T* values, Index nvals) {
-  vec_type_ = GrB_SPARSE;
-  return sparse_.build(indices, values, nvals);
-}
-
-template <typename T>
-Info Vector<T>::build(T* values, Index nvals) {
-  vec_type_ = GrB_DENSE;
-  return dense_.build(values, nvals);
-}
-
-template <typename T>
-Info Vector<T>::setElement(T val, Index index) {
-  if (vec_type_ == GrB_SPARSE)      return sparse_.setElement(val, index);
-  else if (vec_type_ == GrB_DENSE)  return dense_.setElement(val, index);
-  return GrB_UNINITIALIZED_OBJECT;
-}
-
-template <typename T>
-Info Vector<T>::extractElement(T* val, Index index) {
-  if (vec_type_ == GrB_SPARSE)      return sparse_.extractElement(val, index);
-  else if (vec_type_ == GrB_DENSE)  return dense_.extractElement(val, index);
-  return GrB_UNINITIALIZED_OBJECT;
-}
-
-template <typename T>
-Info Vector<T>::extractTuples(std::vector<Index>* indices, std::vector<T>* values,
-    Index* n) {
-  if (vec_type_ == GrB_SPARSE)
-    return sparse_.extractTuples(indices, values, n);
-  else if (vec_type_ == GrB_DENSE)
-    return dense_.extractTuples(indices, values, n);
-  return GrB_UNINITIALIZED_OBJECT;
-}
-
-// A sparse vector is densified with fill value 0 first (reference :208-217).
-template <typename T>
-Info Vector<T>::extractTuples(std::vector<T>* values, Index* n) {
-  if (vec_type_ == GrB_SPARSE) {
-    CHECK(sparse2dense(0.f));
-    return dense_.extractTuples(values, n);
-  } else if (vec_type_ == GrB_DENSE) {
-    return dense_.extractTuples(values, n);
-  }
-  return GrB_UNINITIALIZED_OBJECT;
-}
-
-template <typename T>
-const T& Vector<T>::operator[](Index ind) {
-  static T zero = T();
-  if (vec_type_ == GrB_SPARSE)      return sparse_[ind];
-  else if (vec_type_ == GrB_DENSE)  return dense_[ind];
-  return zero;
-}
-
-template <typename T>
-Info Vector<T>::resize(Index nvals) {
-  if (vec_type_ == GrB_SPARSE)      return sparse_.resize(nvals);
-  else if (vec_type_ == GrB_DENSE)  return dense_.resize(nvals);
-  return GrB_UNINITIALIZED_OBJECT;
-}
-
-template <typename T>
-Info Vector<T>::fill(T val) {
-  if (vec_type_ != GrB_DENSE)
-    CHECK(setStorage(GrB_DENSE));
-  return dense_.fill(val);
-}
-
-template <typename T>
-Info Vector<T>::fillAscending(Index nvals) {
-  if (vec_type_ != GrB_DENSE)
-    CHECK(setStorage(GrB_DENSE));
-  return dense_.fillAscending(nvals);
-}
-
-template <typename T>
-Info Vector<T>::print(bool force_update) {
-  if (vec_type_ == GrB_SPARSE)      return sparse_.print(force_update);
-  else if (vec_type_ == GrB_DENSE)  return dense_.print(force_update);
-  std::cout << "Error: Vector not initialized!\n";
-  return GrB_SUCCESS;
-}
-
-template <typename T>
-Info Vector<T>::countUnique(Index* count) {
-  return GrB_SUCCESS;
-}
 }  // namespace backend
 }  // namespace graphblas
 

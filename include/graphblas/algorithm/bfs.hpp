@@ -3,6 +3,10 @@
 // Operation sequence per level is the reference's (graphblas/algorithm/bfs.hpp:46-79):
 //   assign(v<f1> = level) ; vxm(f2<!v> = f1 (||.&&) A) ; swap(f1,f2) ;
 //   succ = reduce(+, f1) ; stop when succ == 0.
+// With the flags of the reference's benchmark script (run_bfs.sh:8-27) that whole
+// loop runs as ONE cooperative kernel (backend/cuda/bfs_fused.hpp): same levels,
+// no launch or host round trip per level.  GB200_BFS_FUSED=0, --timing 1 or any
+// other flag combination takes the operation-by-operation loop below.
 // Output convention: level of the source is 1, unreached vertices stay 0.
 // Returns the device time of the loop in milliseconds ("tight" in the reference
 // drivers), excluding the initial fill of v.
@@ -20,6 +24,14 @@ namespace algorithm {
 inline float bfs(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor* desc) {
   Index n;
   CHECK(A->nrows(&n));
+  if (backend::bfsFusedApplies(&desc->descriptor_) && A->matrix_.isSparse()) {
+    backend::GpuTimer fused_clock;
+    fused_clock.Start();
+    const Info fused = backend::bfsFused(&v->vector_, &A->matrix_, s,
+                                         &desc->descriptor_, static_cast<int*>(NULL));
+    fused_clock.Stop();
+    if (fused == GrB_SUCCESS) return fused_clock.ElapsedMillis();
+  }
   CHECK(v->fill(0.f));
 
   Vector<float> frontier(n);

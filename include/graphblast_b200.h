@@ -225,6 +225,11 @@ int gb200_reduce_matrix_rows(gb200_vector_t w, int monoid, gb200_matrix_t A,
  * reference drivers, example/gbfs.cu:110-115). */
 int gb200_bfs(gb200_vector_t v, gb200_matrix_t A, int source, gb200_desc_t desc,
               float* tight_ms);                                 /* algorithm/bfs.hpp:14-89 */
+/* Work counters of the last BFS that ran as the fused kernel with this descriptor:
+ * levels, colind entries inspected while pulling, pull levels, frontier entries
+ * pushed, edges pushed, vertices discovered while pushing (all zero if the
+ * traversal ran operation by operation). */
+int gb200_bfs_stats(gb200_desc_t desc, int n, unsigned long long* out6);
 int gb200_sssp(gb200_vector_t v, gb200_matrix_t A, int source, gb200_desc_t desc,
                float* tight_ms);                                /* algorithm/sssp.hpp:15-103 */
 int gb200_pr(gb200_vector_t p, gb200_matrix_t A, float alpha, float eps,

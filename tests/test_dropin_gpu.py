@@ -56,3 +56,44 @@ def test_gtc_unchanged(tmp_path):
     assert out.count("\nCORRECT") == 2 and "INCORRECT" not in out
     assert "Number of triangles: 194" in out
 
+
+
+# ---- the other consumers of the mxv path --------------------
+# Unchanged reference drivers as well; each verifies its result with the reference's
+# own CPU checker (algorithm/test_mis.hpp, test_cc.hpp, test/test.hpp) and prints
+# CORRECT.  gmis / ggc draw random priorities through apply(set_random) on the host,
+# gcc needs assignScatter / extractGather, glgc and gdiameter only vxm + eWise ops.
+
+EXTRA_FLAGS = ["--mxvmode", "0", "--niter", "1", "--timing", "0", "--directed", "2"]
+
+
+def _run_extra(name, tmp_path, more=()):
+    out = run_driver(name, EXTRA_FLAGS + list(more), tmp_path)
+    assert "INCORRECT" not in out, out[-3000:]
+    assert "not implemented" not in out, out[-3000:]
+    return out
+
+
+def test_gmis_unchanged(tmp_path):
+    out = _run_extra("gmis", tmp_path)
+    assert out.count("CORRECT") >= 1, out[-3000:]
+
+
+def test_gcc_unchanged(tmp_path):
+    out = _run_extra("gcc", tmp_path)
+    assert out.count("CORRECT") >= 1, out[-3000:]
+
+
+def test_ggc_unchanged(tmp_path):
+    out = _run_extra("ggc", tmp_path)
+    assert out.count("CORRECT") >= 1, out[-3000:]
+
+
+def test_glgc_unchanged(tmp_path):
+    out = _run_extra("glgc", tmp_path)
+    assert out.count("CORRECT") >= 1, out[-3000:]
+
+
+def test_gdiameter_unchanged(tmp_path):
+    out = _run_extra("gdiameter", tmp_path)
+    assert "Error" not in out, out[-3000:]
