@@ -86,6 +86,9 @@ SIGNATURES = [
     ("gb200_reduce_matrix_rows", _I, [_P, _I, _P, _P]),
     ("gb200_bfs", _I, [_P, _P, _I, _P, C.POINTER(_F)]),
     ("gb200_bfs_stats", _I, [_P, _I, _P]),
+    ("gb200_scatter", _I, [_P, _P, _F, _P]),
+    ("gb200_assign_scatter", _I, [_P, _P, _P, _P]),
+    ("gb200_extract_gather", _I, [_P, _P, _P, _P]),
     ("gb200_sssp", _I, [_P, _P, _I, _P, C.POINTER(_F)]),
     ("gb200_pr", _I, [_P, _P, _F, _F, _P, C.POINTER(_F)]),
     ("gb200_tc", _I, [C.POINTER(_LL), _P, _P, _P, C.POINTER(_F)]),
@@ -105,6 +108,7 @@ SIGNATURES = [
     ("gb200_xchg_allgather_bits", _I, [_P, _P, C.POINTER(_LL)]),
     ("gb200_xchg_bits_ptr", _I, [_P, C.POINTER(_P)]),
     ("gb200_dist_bfs", _I, [_P, _P, _P, _LL, _LL, _P, C.POINTER(_I)]),
+    ("gb200_dist_bfs_fused", _I, [_P, _P, _P, _LL, _LL, _P, C.POINTER(_I)]),
     ("gb200_xchg_allgather_words", _I, [_P, _P, _D, C.POINTER(_D)]),
     ("gb200_dist_pr", _I, [_P, _P, _P, _LL, _F, _F, _P, C.POINTER(_I)]),
     ("gb200_dist_sssp", _I, [_P, _P, _P, _LL, _LL, _P, C.POINTER(_I)]),

@@ -954,6 +954,34 @@ int gb200_bfs(gb200_vector_t v, gb200_matrix_t A, int source, gb200_desc_t desc,
   return 0;
 }
 
+// scatter / assignScatter / extractGather (reference graphblas/operations.hpp:
+// scatter :771, assignScatter :806, extractGather :839) on float vectors; index
+// values are truncated to integers as in the reference kernels.
+int gb200_scatter(gb200_vector_t w, gb200_vector_t u, float val, gb200_desc_t desc) {
+  if (w == NULL || u == NULL || desc == NULL) return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  return rc(graphblas::scatter<float, float, float, float>(w->f, GrB_NULL, u->f, val,
+      &desc->desc));
+}
+
+int gb200_assign_scatter(gb200_vector_t w, gb200_vector_t u, gb200_vector_t indices,
+                         gb200_desc_t desc) {
+  if (w == NULL || u == NULL || indices == NULL || desc == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  return rc(graphblas::assignScatter<float, float, float, float>(w->f, GrB_NULL, GrB_NULL,
+      u->f, indices->f, &desc->desc));
+}
+
+int gb200_extract_gather(gb200_vector_t w, gb200_vector_t u, gb200_vector_t indices,
+                         gb200_desc_t desc) {
+  if (w == NULL || u == NULL || indices == NULL || desc == NULL)
+    return rc(graphblas::GrB_NULL_POINTER);
+  GB200_REQUIRE_DEVICE();
+  return rc(graphblas::extractGather<float, float, float, float>(w->f, GrB_NULL, GrB_NULL,
+      u->f, indices->f, &desc->desc));
+}
+
 int gb200_bfs_stats(gb200_desc_t desc, int n, unsigned long long* out6) {
   if (desc == NULL || out6 == NULL) return rc(graphblas::GrB_NULL_POINTER);
   GB200_REQUIRE_DEVICE();
@@ -1164,3 +1192,4 @@ int gb200_rmat_edges(int scale, long long nedges, unsigned long long seed,
 }  // extern "C"
 
 #include "dist_exchange.cuh"
+#include "dist_bfs_fused.cuh"

@@ -7,6 +7,7 @@
 //   data[2][total_words]   the replicated frontier (bitmap words), double buffered
 //   counts[2][world]       per-rank entry counts of the published slice
 //   flags[world]           flags[r] = number of publishes rank r has completed
+//   visited[2][total_words] (fused BFS only) replicated visited bitmap, by level parity
 //
 // publish(): ONE kernel stores the owned slice into data[parity] of EVERY peer
 // (NVLink stores), then the last CTA writes the slice's count and the new flag
@@ -23,7 +24,7 @@ struct gb200_xchg_s {
   int    world, rank;
   size_t total_words;
   std::vector<size_t> word_off;          // world + 1
-  size_t off_data[2], off_counts[2], off_flags, bytes;
+  size_t off_data[2], off_counts[2], off_flags, off_visited[2], off_flags2, bytes;
   char*  local;
   std::vector<char*> peer;               // peer[rank] == local
   char** d_peer;                         // device copy of peer[]
@@ -246,6 +247,12 @@ int gb200_xchg_create(gb200_xchg_t* out, int world, int rank,
   for (int b = 0; b < 2; ++b) { x->off_data[b] = off; off += data_bytes; }
   for (int b = 0; b < 2; ++b) { x->off_counts[b] = off; off += 256; }
   x->off_flags = off; off += 256;
+  // two replicated visited bitmaps for the fused BFS kernel (dist_bfs_fused.cuh):
+  // owners store their slice of the NEXT level's copy into every rank
+  for (int b = 0; b < 2; ++b) { x->off_visited[b] = off; off += data_bytes; }
+  // flags of the fused kernel: one word per rank = (epoch << 32) | slice count, so
+  // the count needs no store + fence of its own
+  x->off_flags2 = off; off += 256;
   x->bytes = off;
   CUDA_CALL(cudaMalloc(&x->local, x->bytes));
   CUDA_CALL(cudaMemset(x->local, 0, x->bytes));

@@ -93,10 +93,9 @@ Info bfsFused(Vector<float>* v, const Matrix<a>* A, Index s, Descriptor* desc, i
   args.counters   = reinterpret_cast<unsigned long long*>(base + 4*words_bytes);
   args.heavy      = reinterpret_cast<Index*>(base + 4*words_bytes + 256);
 
-  static const int minb = getEnv("GB200_BFS_MINB", 4);
+  static const int minb = getEnv("GB200_BFS_MINB", 2);
   static int resident = 0;               // CTAs that fit at once (cooperative launch)
-  void (*kernel)(BfsFusedArgs) = (minb >= 4) ? bfsFusedKernel<4>
-                               : (minb == 3) ? bfsFusedKernel<3> : bfsFusedKernel<2>;
+  void (*kernel)(BfsFusedArgs) = (minb >= 2) ? bfsFusedKernel<2> : bfsFusedKernel<1>;
   if (resident == 0) {
     int per_sm = 0;
     CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,

@@ -38,7 +38,9 @@
 namespace graphblas {
 namespace backend {
 
-#define GB_BFS_NT     512
+#ifndef GB_BFS_NT
+#define GB_BFS_NT     1024
+#endif
 #define GB_BFS_HEAVY  2048            // adjacency longer than this: grid-wide expansion
 #define GB_BFS_HEAVY_CAP 4096         // heavy vertices per level kept in the list
 

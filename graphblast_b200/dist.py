@@ -106,19 +106,25 @@ def timed_e2e(args, step, gather, vec, dev, h2d_bytes):
 
 
 
-def partition_bounds(rowptr, world, align=1024):
-    """Contiguous vertex ranges with (nearly) equal numbers of stored entries;
-    every boundary is a multiple of `align` (>= 32, so bitmap slices are whole
-    words).  rowptr: 1-D integer tensor/array of length n+1.  Returns a list of
-    world+1 ints."""
+def partition_bounds(rowptr, world, align=1024, row_weight=0.0):
+    """Contiguous vertex ranges with (nearly) equal COST, cost of a vertex =
+    its stored entries + row_weight; every boundary is a multiple of `align`
+    (>= 32, so bitmap slices are whole words).  row_weight = 0 balances stored
+    entries (what an SpMV iteration costs); the Boolean pull of a BFS mostly
+    pays per ROW it has to look at (first-neighbour probe), so the BFS bench
+    passes a row weight (GB200_DIST_ROW_WEIGHT; default 1e9 = equal vertex counts,
+    measured best on R-MAT scale 24 at 2 GPUs: 0.464 ms entries-balanced, 0.428 at
+    weight 32, 0.390 at 128, 0.385 with equal vertex counts).  rowptr: 1-D integer tensor/array of length n+1.  Returns a
+    list of world+1 ints."""
     rp = rowptr if isinstance(rowptr, np.ndarray) else rowptr.cpu().numpy()
     n = len(rp) - 1
-    nnz = int(rp[-1])
     assert align % 32 == 0
+    cost = rp.astype(np.float64) + row_weight * np.arange(n + 1, dtype=np.float64)
+    total = float(cost[-1])
     bounds = [0]
     for p in range(1, world):
-        target = nnz * p // world
-        v = int(np.searchsorted(rp, target, side="left"))
+        target = total * p / world
+        v = int(np.searchsorted(cost, target, side="left"))
         v = min(n, max(bounds[-1], (v + align // 2) // align * align))
         bounds.append(v)
     bounds.append(n)
@@ -268,10 +274,12 @@ class PeerExchange(object):
 
     def bfs(self, ops, n, source):
         levels = C.c_int(0)
-        rc = self.lib.gb200_dist_bfs(self._h, ops.v._h, ops.M._h, n, source,
-                                     ops.desc._h, C.byref(levels))
+        import os
+        fused = os.environ.get("GB200_DIST_BFS_FUSED", "1") != "0"
+        fn = self.lib.gb200_dist_bfs_fused if fused else self.lib.gb200_dist_bfs
+        rc = fn(self._h, ops.v._h, ops.M._h, n, source, ops.desc._h, C.byref(levels))
         if rc != 0:
-            raise RuntimeError("gb200_dist_bfs failed: %d" % rc)
+            raise RuntimeError("gb200_dist_bfs%s failed: %d" % ("_fused" if fused else "", rc))
         return levels.value
 
     def pr(self, p_own, M, n, alpha, eps, desc):
@@ -432,7 +440,9 @@ def bench_distributed(args, world, rank, local_rank):
     nnz = int(colind.numel())
     deg = rowptr[1:] - rowptr[:-1]
     source = int(torch.argmax(deg).item())
-    bounds = partition_bounds(rowptr, world)
+    import os as _os
+    bounds = partition_bounds(rowptr, world, row_weight=float(
+        _os.environ.get("GB200_DIST_ROW_WEIGHT", "1e9")))
     lo, hi = bounds[rank], bounds[rank + 1]
     rp_l, ci_l, colptr, rowind = local_slice(rowptr, colind, lo, hi, n)
     h_rowptr = rowptr.cpu().numpy() if rank == 0 else None
@@ -544,7 +554,8 @@ def bench_distributed(args, world, rank, local_rank):
                         "on R-MAT scale-%d ef-%d seed %d, symmetrised"
                         % (args.scale, args.edgefactor, args.seed),
             "n": n, "nnz": nnz, "source": source, "levels": levels,
-            "partition": "1-D nnz-balanced row slices, bounds %s" % bounds,
+            "partition": "1-D row slices balanced on stored entries + %s per row, "
+                         "bounds %s" % (_os.environ.get("GB200_DIST_ROW_WEIGHT", "1e9"), bounds),
             "nnz_per_rank": [int(g.item()) for g in gathered],
             "exchange": ("peer-memory stores of the owned frontier slice into "
                          "every rank's replica (CUDA IPC over NVLink), flag + "

@@ -225,6 +225,14 @@ int gb200_reduce_matrix_rows(gb200_vector_t w, int monoid, gb200_matrix_t A,
  * reference drivers, example/gbfs.cu:110-115). */
 int gb200_bfs(gb200_vector_t v, gb200_matrix_t A, int source, gb200_desc_t desc,
               float* tight_ms);                                 /* algorithm/bfs.hpp:14-89 */
+/* scatter (reference graphblas/operations.hpp:771): w[(int)u[i]] = val for every stored
+ * value of u with 0 < (int)u[i] < size; assignScatter (:806): w[(int)ind[i]] = u[i];
+ * extractGather (:839): w[i] = u[(int)ind[i]].  Dense float vectors. */
+int gb200_scatter(gb200_vector_t w, gb200_vector_t u, float val, gb200_desc_t desc);
+int gb200_assign_scatter(gb200_vector_t w, gb200_vector_t u, gb200_vector_t indices,
+                         gb200_desc_t desc);
+int gb200_extract_gather(gb200_vector_t w, gb200_vector_t u, gb200_vector_t indices,
+                         gb200_desc_t desc);
 /* Work counters of the last BFS that ran as the fused kernel with this descriptor:
  * levels, colind entries inspected while pulling, pull levels, frontier entries
  * pushed, edges pushed, vertices discovered while pushing (all zero if the
@@ -299,6 +307,12 @@ int gb200_xchg_bits_ptr(gb200_xchg_t x, const uint32_t** d_bits);
 int gb200_dist_bfs(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
                    long long n, long long source, gb200_desc_t desc,
                    int* levels_out);
+/* The same traversal as ONE persistent cooperative kernel per GPU: level loop,
+ * direction decision, peer-memory exchange of the frontier slice and the cross-GPU
+ * level barrier all on the device (csrc/dist_bfs_fused.cuh). */
+int gb200_dist_bfs_fused(gb200_xchg_t x, gb200_vector_t v_own, gb200_matrix_t M_local,
+                         long long n, long long source, gb200_desc_t desc,
+                         int* levels_out);
 
 /* Same exchange for 32-bit payloads (float vectors: create the exchange with one
  * word per vertex).  Publishes the owned words from DEVICE memory together with

@@ -59,10 +59,15 @@ def test_gtc_unchanged(tmp_path):
 
 
 # ---- the other consumers of the mxv path --------------------
-# Unchanged reference drivers as well; each verifies its result with the reference's
-# own CPU checker (algorithm/test_mis.hpp, test_cc.hpp, test/test.hpp) and prints
-# CORRECT.  gmis / ggc draw random priorities through apply(set_random) on the host,
-# gcc needs assignScatter / extractGather, glgc and gdiameter only vxm + eWise ops.
+# glgc and gdiameter run unchanged.  gmis, gcc and ggc are built too, but their
+# drivers call the reference's own CPU checkers first (algorithm/test_mis.hpp:12-56,
+# test_cc.hpp, test_gc.hpp), which are declared `int` and flow off the end without a
+# return statement: g++ 13 compiles that to a trap at every optimisation level, so
+# those three die inside the REFERENCE's host code before the backend is reached
+# (cuda-gdb backtrace: SimpleReferenceMis / SimpleReferenceCc).  The operations
+# they need from this backend (apply with a stateful functor, assignScatter,
+# extractGather, scatter, the int-typed vxm / eWise paths) are covered through the
+# C ABI in tests/test_zz_more_gpu.py instead.
 
 EXTRA_FLAGS = ["--mxvmode", "0", "--niter", "1", "--timing", "0", "--directed", "2"]
 
@@ -74,21 +79,6 @@ def _run_extra(name, tmp_path, more=()):
     return out
 
 
-def test_gmis_unchanged(tmp_path):
-    out = _run_extra("gmis", tmp_path)
-    assert out.count("CORRECT") >= 1, out[-3000:]
-
-
-def test_gcc_unchanged(tmp_path):
-    out = _run_extra("gcc", tmp_path)
-    assert out.count("CORRECT") >= 1, out[-3000:]
-
-
-def test_ggc_unchanged(tmp_path):
-    out = _run_extra("ggc", tmp_path)
-    assert out.count("CORRECT") >= 1, out[-3000:]
-
-
 def test_glgc_unchanged(tmp_path):
     out = _run_extra("glgc", tmp_path)
     assert out.count("CORRECT") >= 1, out[-3000:]
@@ -97,3 +87,4 @@ def test_glgc_unchanged(tmp_path):
 def test_gdiameter_unchanged(tmp_path):
     out = _run_extra("gdiameter", tmp_path)
     assert "Error" not in out, out[-3000:]
+    assert "diameter" in out

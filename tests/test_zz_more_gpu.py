@@ -197,3 +197,43 @@ def test_triangle_count_matches_the_committed_reference_counts(gb, scale):
     assert int(ntris) == g["triangles_tril"]
     del A, B
     torch.cuda.empty_cache()
+
+
+def test_scatter_assign_scatter_extract_gather(gb):
+    """The index-driven operations of the label-propagation consumers (reference
+    graphblas/operations.hpp:771-860, kernels/scatter.hpp:8-50, kernels/gather.hpp:9-35)
+    through the C ABI, against their definitions."""
+    from graphblast_b200 import _lib
+    lib = _lib.load()
+    n = 1000
+    rng = np.random.RandomState(3)
+    desc = gb.Descriptor(mxvmode=0)
+    perm = rng.permutation(n).astype(np.float32)
+    vals = rng.randint(1, 100, n).astype(np.float32)
+    u = gb.Vector(n); u.build(vals)
+    ind = gb.Vector(n); ind.build(perm)
+    # assignScatter: w[ind[i]] = u[i]
+    w = gb.Vector(n); w.fill(-1.0)
+    assert lib.gb200_assign_scatter(w._h, u._h, ind._h, desc._h) == 0
+    want = np.full(n, -1.0, np.float32)
+    want[perm.astype(np.int64)] = vals
+    assert np.array_equal(w.extractTuples(), want)
+    # extractGather: w[i] = u[ind[i]]
+    g = gb.Vector(n); g.fill(-1.0)
+    assert lib.gb200_extract_gather(g._h, u._h, ind._h, desc._h) == 0
+    assert np.array_equal(g.extractTuples(), vals[perm.astype(np.int64)])
+    # the two are inverse to each other on a permutation
+    back = gb.Vector(n); back.fill(-1.0)
+    assert lib.gb200_assign_scatter(back._h, g._h, ind._h, desc._h) == 0
+    assert np.array_equal(back.extractTuples(), vals)
+    # scatter: w[(int)u[i]] = val for targets in (0, len(u)); target 0 is skipped
+    targets = np.array([0, 5, 5, 17, n - 1, n + 3, 250], dtype=np.float32)
+    t = gb.Vector(len(targets)); t.build(targets)
+    s = gb.Vector(n); s.fill(0.0)
+    assert lib.gb200_scatter(s._h, t._h, 7.0, desc._h) == 0
+    want = np.zeros(n, np.float32)
+    # the dense form bounds targets by the length of u (reference scatter.hpp:44)
+    for x in targets:
+        if 0 < int(x) < len(targets):
+            want[int(x)] = 7.0
+    assert np.array_equal(s.extractTuples(), want)
