@@ -79,6 +79,21 @@ Info settle(const Vector<X>* x, Rest... rest) {
   return settle(rest...);
 }
 
+// Operations that exist in the frontend but that no algorithm of the path reaches
+// (SURVEY.md §8b "must declare"): whatever the call shape — the frontend names the
+// template arguments of some of them explicitly — the answer is the same.
+#define GB_DECLARED_ONLY(name, what)                                        \
+  template <typename... Named, typename... Args>                            \
+  Info name(Args... args) { return notBuilt(what); }
+
+GB_DECLARED_ONLY(extract,           "extract of a vector")
+GB_DECLARED_ONLY(assignIndexed,     "assignIndexed")
+GB_DECLARED_ONLY(transpose,         "transpose")
+GB_DECLARED_ONLY(traceMxmTranspose, "traceMxmTranspose")
+GB_DECLARED_ONLY(graphColor,        "graphColor (cuSPARSE csrcolor, gone from CUDA 12)")
+GB_DECLARED_ONLY(applyVxm,          "applyVxm")
+#undef GB_DECLARED_ONLY
+
 template <typename c, typename a, typename b, typename m,
           typename BinaryOpT,     typename SemiringT>
 Info mxm(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
@@ -90,138 +105,111 @@ Info mxm(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
 }
 
 // Shared body of vxm / mxv once the descriptor says which side is transposed.
+// Step 1 puts the input vector into the storage the direction needs, step 2 runs
+// the push (sparse input) or the pull (dense input).
 template <bool IsVxm, typename W, typename U, typename a, typename M,
           typename BinaryOpT, typename SemiringT>
 Info mxvDispatch(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
     const Matrix<a>* A, const Vector<U>* u, Descriptor* desc) {
-  Vector<U>* u_t = const_cast<Vector<U>*>(u);
+  Vector<U>* input = const_cast<Vector<U>*>(u);
+  if (!A->isSparse()) return notBuilt("mxv / vxm with a dense matrix (GEMV)");
 
-  Storage u_vec_type;
-  Storage A_mat_type;
-  CHECK(u->getStorage(&u_vec_type));
-  CHECK(A->getStorage(&A_mat_type));
+  SparseMatrixFormat format;
+  bool reported_symmetric;
+  Desc_value mode;
+  CHECK(A->getFormat(&format));
+  CHECK(A->getSymmetry(&reported_symmetric));
+  CHECK(desc->get(GrB_MXVMODE, &mode));
+  const bool one_orientation = !reported_symmetric && format == GrB_SPARSE_MATRIX_CSRONLY;
+  const bool both_orientations = reported_symmetric || format == GrB_SPARSE_MATRIX_CSRCSC;
 
-  LoadBalanceMode lb_mode = getEnv("GRB_LOAD_BALANCE_MODE",
-      GrB_LOAD_BALANCE_MERGE);
-
-  SparseMatrixFormat A_format;
-  bool A_symmetric;
-  CHECK(A->getFormat(&A_format));
-  CHECK(A->getSymmetry(&A_symmetric));
-
-  Desc_value mxv_mode;
-  CHECK(desc->get(GrB_MXVMODE, &mxv_mode));
-
-  // Conversions of the input vector decide the direction.
-  if (!A_symmetric && A_format == GrB_SPARSE_MATRIX_CSRONLY) {
-    if (IsVxm) {
-      if (u_vec_type == GrB_DENSE)
-        CHECK(u_t->dense2sparse(op.identity(), desc));
-    } else {
-      if (u_vec_type == GrB_SPARSE)
-        CHECK(u_t->sparse2dense(op.identity(), desc));
+  // ---- step 1: storage of the input ------------------------------------------------
+  const U identity = op.identity();
+  const bool dense_in = (input->vec_type_ == GrB_DENSE);
+  const bool sparse_in = (input->vec_type_ == GrB_SPARSE);
+  if (one_orientation) {
+    // only the CSR exists: vxm can only push over it, mxv can only pull over it
+    if (IsVxm && dense_in)   CHECK(input->dense2sparse(identity, desc));
+    if (!IsVxm && sparse_in) CHECK(input->sparse2dense(identity, desc));
+  } else {
+    switch (mode) {
+      case GrB_PUSHPULL: CHECK(input->convert(identity, desc->switchpoint(), desc)); break;
+      case GrB_PUSHONLY: if (dense_in)  CHECK(input->dense2sparse(identity, desc)); break;
+      case GrB_PULLONLY: if (sparse_in) CHECK(input->sparse2dense(identity, desc)); break;
+      default: break;
     }
-  } else if (mxv_mode == GrB_PUSHPULL) {
-    CHECK(u_t->convert(op.identity(), desc->switchpoint(), desc));
-  } else if (mxv_mode == GrB_PUSHONLY && u_vec_type == GrB_DENSE) {
-    CHECK(u_t->dense2sparse(op.identity(), desc));
-  } else if (mxv_mode == GrB_PULLONLY && u_vec_type == GrB_SPARSE) {
-    CHECK(u_t->sparse2dense(op.identity(), desc));
   }
-  CHECK(u->getStorage(&u_vec_type));
 
-  bool run_pull = !(A_mat_type == GrB_SPARSE && u_vec_type == GrB_SPARSE);
-  if (!run_pull) {
-    if (lb_mode == GrB_LOAD_BALANCE_MERGE) {
-      // w becomes a sparse vector only if the push really runs: on a hand-back
-      // its previous storage (and with it a dense w that accum combines into) must
-      // survive untouched, so the tag is restored below.
-      Storage w_before;
-      CHECK(w->getStorage(&w_before));
-      CHECK(w->setStorage(GrB_SPARSE));
-      // In the automatic mode the push may hand the call back when the frontier
-      // owns too many of the edges (spmspv.hpp); both orientations must exist.
-      bool prefer_pull = false;
-      const bool may_switch = (mxv_mode == GrB_PUSHPULL) &&
-          (A_symmetric || A_format == GrB_SPARSE_MATRIX_CSRCSC);
-      CHECK(spmspvMerge(&w->sparse_, mask, accum, op,
-          &A->sparse_, &u->sparse_, desc, may_switch ? &prefer_pull : NULL));
-      if (prefer_pull) {
-        w->vec_type_ = w_before;
-        CHECK(u_t->sparse2dense(op.identity(), desc));
-        run_pull = true;
-      }
-    } else if (lb_mode == GrB_LOAD_BALANCE_SIMPLE) {
-      std::cout << "Simple SPMSPV not implemented yet!\n";
-      return GrB_NOT_IMPLEMENTED;
-    } else if (lb_mode == GrB_LOAD_BALANCE_TWC) {
-      std::cout << "Error: B40C load-balance algorithm not implemented yet!\n";
-      return GrB_NOT_IMPLEMENTED;
+  // ---- step 2: push ------------------------------------------------------------------
+  bool pull = (input->vec_type_ != GrB_SPARSE);
+  if (!pull) {
+    const LoadBalanceMode balance = getEnv("GRB_LOAD_BALANCE_MODE", GrB_LOAD_BALANCE_MERGE);
+    if (balance != GrB_LOAD_BALANCE_MERGE)
+      return notBuilt("push load balancing other than GrB_LOAD_BALANCE_MERGE");
+    // w becomes a sparse vector only if the push really runs: on a hand-back its
+    // previous storage (and with it a dense w that accum combines into) must
+    // survive untouched, so the tag is restored below.
+    const Storage w_before = w->vec_type_;
+    CHECK(w->setStorage(GrB_SPARSE));
+    // In the automatic mode the push may hand the call back when the frontier owns
+    // too many of the edges (spmspv.hpp); both orientations must exist for that.
+    bool hand_back = false;
+    const bool may_hand_back = (mode == GrB_PUSHPULL) && both_orientations;
+    CHECK(spmspvMerge(&w->sparse_, mask, accum, op, &A->sparse_, &u->sparse_, desc,
+        may_hand_back ? &hand_back : NULL));
+    if (hand_back) {
+      w->vec_type_ = w_before;
+      CHECK(input->sparse2dense(identity, desc));
+      pull = true;
     } else {
-      std::cout << "Error: Invalid load-balance algorithm!\n";
+      desc->lastmxv_ = GrB_PUSHONLY;
     }
-    if (!run_pull) desc->lastmxv_ = GrB_PUSHONLY;
   }
-  if (run_pull) {
+  // ---- step 2: pull ------------------------------------------------------------------
+  if (pull) {
     if (IsVxm) CHECK(w->setStorage(GrB_DENSE));
-    else       CHECK(w->sparse2dense(op.identity(), desc));
-    if (A_mat_type == GrB_SPARSE) {
-      CHECK(spmv(&w->dense_, mask, accum, op, &A->sparse_, &u->dense_, desc));
-    } else {
-      std::cout << "Error: GEMV not implemented yet!\n";
-      return GrB_NOT_IMPLEMENTED;
-    }
+    else       CHECK(w->sparse2dense(identity, desc));
+    CHECK(spmv(&w->dense_, mask, accum, op, &A->sparse_, &u->dense_, desc));
     desc->lastmxv_ = GrB_PULLONLY;
   }
   return GrB_SUCCESS;
 }
 
+// Debug trace shared by the two entry points.
+template <typename X>
+void traceVector(Descriptor* desc, const char* banner, const Vector<X>* x) {
+  if (!desc->debug()) return;
+  std::cout << banner << "\n";
+  const_cast<Vector<X>*>(x)->print();
+}
+
+// vxm = mxv on the transposed matrix: GrB_INP1 is toggled around the call.
 template <typename W, typename U, typename a, typename M,
           typename BinaryOpT, typename SemiringT>
 Info vxm(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
     const Vector<U>* u, const Matrix<a>* A, Descriptor* desc) {
-  if (desc->debug()) {
-    std::cout << "===Begin vxm===\n";
-    CHECK(const_cast<Vector<U>*>(u)->print());
-  }
-
+  traceVector(desc, "===Begin vxm===", u);
   Desc_value inp0_mode;
   CHECK(desc->get(GrB_INP0, &inp0_mode));
   if (inp0_mode != GrB_DEFAULT) return GrB_INVALID_VALUE;
-
-  // Treat vxm as an mxv with transposed matrix
   CHECK(desc->toggle(GrB_INP1));
-  Info err = mxvDispatch<true>(w, mask, accum, op, A, u, desc);
+  const Info status = mxvDispatch<true>(w, mask, accum, op, A, u, desc);
   CHECK(desc->toggle(GrB_INP1));
-  if (err != GrB_SUCCESS) return err;
-
-  if (desc->debug()) {
-    std::cout << "===End vxm===\n";
-    CHECK(w->print());
-  }
-  return GrB_SUCCESS;
+  if (status == GrB_SUCCESS) traceVector(desc, "===End vxm===", w);
+  return status;
 }
 
 template <typename W, typename a, typename U, typename M,
           typename BinaryOpT, typename SemiringT>
 Info mxv(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
     const Matrix<a>* A, const Vector<U>* u, Descriptor* desc) {
-  if (desc->debug()) {
-    std::cout << "===Begin mxv===\n";
-    CHECK(const_cast<Vector<U>*>(u)->print());
-  }
-
+  traceVector(desc, "===Begin mxv===", u);
   Desc_value inp1_mode;
   CHECK(desc->get(GrB_INP1, &inp1_mode));
   if (inp1_mode != GrB_DEFAULT) return GrB_INVALID_VALUE;
-
-  CHECK((mxvDispatch<false>(w, mask, accum, op, A, u, desc)));
-
-  if (desc->debug()) {
-    std::cout << "===End mxv===\n";
-    CHECK(w->print());
-  }
-  return GrB_SUCCESS;
+  const Info status = mxvDispatch<false>(w, mask, accum, op, A, u, desc);
+  if (status == GrB_SUCCESS) traceVector(desc, "===End mxv===", w);
+  return status;
 }
 
 // w = u .* v.  Results: dense x dense -> dense (sparse when the mask is sparse),
@@ -351,20 +339,6 @@ Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op
   return eWiseAddInner(&w->dense_, mask, accum, op, &u->sparse_, val, desc);
 }
 
-template <typename W, typename U, typename M,
-          typename BinaryOpT>
-Info extract(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, const Vector<U>* u,
-    const std::vector<Index>* indices, Index nindices, Descriptor* desc) {
-  return notBuilt("extract of a vector");
-}
-
-template <typename W, typename U, typename M,
-          typename BinaryOpT>
-Info assignIndexed(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
-    const Vector<U>* u, int* indices, Index nindices, Descriptor* desc) {
-  return notBuilt("assignIndexed");
-}
-
 // Masked constant assign.  The target is written in part, so its lazily held
 // values are written out first; a dense mask is read through its bitmap shadow
 // when that is current, except by the sparse-target filter, which reads values.
@@ -452,20 +426,6 @@ Info reduce(T* val, BinaryOpT accum, MonoidT op, const Matrix<a>* A, Descriptor*
   return GrB_UNINITIALIZED_OBJECT;
 }
 
-template <typename c, typename a, typename m,
-          typename BinaryOpT>
-Info transpose(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, const Matrix<a>* A,
-    Descriptor* desc) {
-  return notBuilt("transpose");
-}
-
-template <typename T, typename a, typename b,
-          typename SemiringT>
-Info traceMxmTranspose(T* val, SemiringT op, const Matrix<a>* A, const Matrix<b>* B,
-    Descriptor* desc) {
-  return notBuilt("traceMxmTranspose");
-}
-
 // ---- index-driven vector operations (indexed.hpp) ------------------------------
 
 template <typename W, typename M, typename U, typename T>
@@ -486,18 +446,6 @@ template <typename W, typename U, typename M, typename I,
 Info extractGather(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
     const Vector<U>* u, const Vector<I>* indices, Descriptor* desc) {
   return indexedMove<true>(w, mask, u, indices, desc);
-}
-
-template <typename W, typename a>
-Info graphColor(Vector<W>* w, const Matrix<a>* A, Descriptor* desc) {
-  return notBuilt("graphColor (cuSPARSE csrcolor, gone from CUDA 12)");
-}
-
-template <typename W, typename U, typename a, typename M,
-          typename BinaryOpT, typename SemiringT>
-Info applyVxm(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
-    const Vector<U>* u, const Matrix<a>* A, Descriptor* desc) {
-  return notBuilt("applyVxm");
 }
 
 template <typename c, typename a>

@@ -166,36 +166,31 @@ class Vector {
 
 // ---- storage state and conversions (the direction switch lives here) ----
 
+// The direction switch.  fill = stored entries / length of the vector in its current
+// storage.  A sparse vector turns dense once fill exceeds the switch point while
+// still growing; a dense one turns sparse once fill is at or below it while
+// shrinking; otherwise only the fill seen is remembered (hysteresis of reference
+// vector.hpp:292-323).
 template <typename T>
 Info Vector<T>::convert(T identity, float switchpoint, Descriptor* desc) {
-  Index nvals_t;
-  Index nsize_t;
-  if (vec_type_ == GrB_SPARSE) {
-    CHECK(sparse_.nvals(&nvals_t));
-    CHECK(sparse_.size(&nsize_t));
-  } else if (vec_type_ == GrB_DENSE) {
-    CHECK(dense_.computeNnz(&nvals_t, identity, desc));
-    CHECK(dense_.nvals(&nsize_t));
+  if (vec_type_ != GrB_SPARSE && vec_type_ != GrB_DENSE) return GrB_UNINITIALIZED_OBJECT;
+  const bool sparse_now = (vec_type_ == GrB_SPARSE);
+  Index entries = 0, length = 0;
+  if (sparse_now) {
+    CHECK(sparse_.nvals(&entries));
+    CHECK(sparse_.size(&length));
   } else {
-    return GrB_UNINITIALIZED_OBJECT;
+    CHECK(dense_.computeNnz(&entries, identity, desc));
+    CHECK(dense_.nvals(&length));
   }
-
-  float ratio = static_cast<float>(nvals_t)/nsize_t;
+  const float fill = static_cast<float>(entries)/length;
   if (desc->dirinfo())
-    std::cout << "Nnz ratio: " << ratio << " Switch point: "
-        << switchpoint << std::endl;
-
-  if (vec_type_ == GrB_SPARSE) {
-    if (ratio > switchpoint && ratio > ratio_)
-      CHECK(sparse2dense(identity, desc));
-    else
-      ratio_ = ratio;
-  } else if (vec_type_ == GrB_DENSE) {
-    if (ratio <= switchpoint && ratio < ratio_)
-      CHECK(dense2sparse(identity, desc));
-    else
-      ratio_ = ratio;
-  }
+    std::cout << "Nnz ratio: " << fill << " Switch point: " << switchpoint << std::endl;
+  const bool to_dense  = sparse_now  && fill >  switchpoint && fill > ratio_;
+  const bool to_sparse = !sparse_now && fill <= switchpoint && fill < ratio_;
+  if (to_dense)  return sparse2dense(identity, desc);
+  if (to_sparse) return dense2sparse(identity, desc);
+  ratio_ = fill;
   return GrB_SUCCESS;
 }
 
