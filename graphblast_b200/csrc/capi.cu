@@ -161,7 +161,14 @@ int gb200_init(int device) {
 
 int gb200_set_stream(void* cuda_stream) {
   GB200_REQUIRE_DEVICE();
-  graphblas::backend::runtime().stream = static_cast<cudaStream_t>(cuda_stream);
+  // Work already queued on the old stream must not be overtaken by work on the
+  // new one (pool frees, cached tiles, scratch arenas are all stream-ordered).
+  graphblas::backend::Runtime& rt = graphblas::backend::runtime();
+  cudaStream_t next = static_cast<cudaStream_t>(cuda_stream);
+  if (next != rt.stream) {
+    if (cudaStreamSynchronize(rt.stream) != cudaSuccess) return rc(graphblas::GrB_PANIC);
+    rt.stream = next;
+  }
   return 0;
 }
 
@@ -949,7 +956,9 @@ int gb200_bfs(gb200_vector_t v, gb200_matrix_t A, int source, gb200_desc_t desc,
   A->f->nrows(&n);
   if (source < 0 || source >= n) return rc(graphblas::GrB_INVALID_INDEX);
   GB200_REQUIRE_DEVICE();
+  graphblas::algorithm::lastStatus() = graphblas::GrB_SUCCESS;
   float ms = graphblas::algorithm::bfs(v->f, A->f, source, &desc->desc);
+  if (ms < 0.f) return rc(graphblas::algorithm::lastStatus());
   if (tight_ms) *tight_ms = ms;
   return 0;
 }
@@ -998,7 +1007,9 @@ int gb200_sssp(gb200_vector_t v, gb200_matrix_t A, int source,
   A->f->nrows(&n);
   if (source < 0 || source >= n) return rc(graphblas::GrB_INVALID_INDEX);
   GB200_REQUIRE_DEVICE();
+  graphblas::algorithm::lastStatus() = graphblas::GrB_SUCCESS;
   float ms = graphblas::algorithm::sssp(v->f, A->f, source, &desc->desc);
+  if (ms < 0.f) return rc(graphblas::algorithm::lastStatus());
   if (tight_ms) *tight_ms = ms;
   return 0;
 }
@@ -1009,7 +1020,9 @@ int gb200_pr(gb200_vector_t p, gb200_matrix_t A, float alpha, float eps,
     return rc(graphblas::GrB_UNINITIALIZED_OBJECT);
   if (A->f == NULL) return rc(graphblas::GrB_DOMAIN_MISMATCH);
   GB200_REQUIRE_DEVICE();
+  graphblas::algorithm::lastStatus() = graphblas::GrB_SUCCESS;
   float ms = graphblas::algorithm::pr(p->f, A->f, alpha, eps, &desc->desc);
+  if (ms < 0.f) return rc(graphblas::algorithm::lastStatus());
   if (tight_ms) *tight_ms = ms;
   return 0;
 }
@@ -1021,7 +1034,9 @@ int gb200_tc(long long* ntris, gb200_matrix_t A, gb200_matrix_t B,
   if (A->i == NULL || B->i == NULL) return rc(graphblas::GrB_DOMAIN_MISMATCH);
   GB200_REQUIRE_DEVICE();
   int count = 0;
+  graphblas::algorithm::lastStatus() = graphblas::GrB_SUCCESS;
   float ms = graphblas::algorithm::tc(&count, A->i, B->i, &desc->desc);
+  if (ms < 0.f) return rc(graphblas::algorithm::lastStatus());
   *ntris = count;
   if (tight_ms) *tight_ms = ms;
   return 0;

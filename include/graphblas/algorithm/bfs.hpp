@@ -23,7 +23,7 @@ namespace algorithm {
 
 inline float bfs(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor* desc) {
   Index n;
-  CHECK(A->nrows(&n));
+  GB_ALGO_STEP(A->nrows(&n));
   if (backend::bfsFusedApplies(&desc->descriptor_) && A->matrix_.isSparse()) {
     backend::GpuTimer fused_clock;
     fused_clock.Start();
@@ -32,20 +32,20 @@ inline float bfs(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor* 
     fused_clock.Stop();
     if (fused == GrB_SUCCESS) return fused_clock.ElapsedMillis();
   }
-  CHECK(v->fill(0.f));
+  GB_ALGO_STEP(v->fill(0.f));
 
   Vector<float> frontier(n);
   Vector<float> next(n);
 
   Desc_value mxv_mode;
-  CHECK(desc->get(GrB_MXVMODE, &mxv_mode));
+  GB_ALGO_STEP(desc->get(GrB_MXVMODE, &mxv_mode));
   if (mxv_mode == GrB_PULLONLY) {
-    CHECK(frontier.fill(0.f));
-    CHECK(frontier.setElement(1.f, s));
+    GB_ALGO_STEP(frontier.fill(0.f));
+    GB_ALGO_STEP(frontier.setElement(1.f, s));
   } else {
     std::vector<Index> src_ind(1, s);
     std::vector<float> src_val(1, 1.f);
-    CHECK(frontier.build(&src_ind, &src_val, 1, GrB_NULL));
+    GB_ALGO_STEP(frontier.build(&src_ind, &src_val, 1, GrB_NULL));
   }
 
   backend::Descriptor& d = desc->descriptor_;
@@ -59,11 +59,11 @@ inline float bfs(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor* 
     unvisited -= static_cast<int>(succ);
     assign<float, float, float, Index>(v, &frontier, GrB_NULL,
         static_cast<float>(level), GrB_ALL, n, desc);
-    CHECK(desc->toggle(GrB_MASK));
+    GB_ALGO_STEP(desc->toggle(GrB_MASK));
     vxm<float, float, float, float>(&next, v, GrB_NULL,
         LogicalOrAndSemiring<float>(), &frontier, A, desc);
-    CHECK(desc->toggle(GrB_MASK));
-    CHECK(next.swap(&frontier));
+    GB_ALGO_STEP(desc->toggle(GrB_MASK));
+    GB_ALGO_STEP(next.swap(&frontier));
     reduce<float, float>(&succ, GrB_NULL, PlusMonoid<float>(), &frontier, desc);
 
     if (verbose) {

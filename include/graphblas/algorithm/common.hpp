@@ -33,6 +33,25 @@ struct set_uniform_random {
 };
 
 namespace algorithm {
+// The drivers return a time in milliseconds, as the reference's do
+// (algorithm/bfs.hpp:18-21), so an Info cannot travel in the return value: a
+// failing step records its status here and the driver returns -1.  Callers
+// that want the code (the C ABI) read lastStatus() after the call.
+inline Info& lastStatus() {
+  static thread_local Info status = GrB_SUCCESS;
+  return status;
+}
+#define GB_ALGO_STEP(x)                                               \
+  do {                                                                \
+    graphblas::Info gb_step__ = (x);                                  \
+    if (gb_step__ != graphblas::GrB_SUCCESS) {                        \
+      fprintf(stderr, "Runtime error: %s returned %d at %s:%d\n",     \
+              #x, gb_step__, __FILE__, __LINE__);                     \
+      graphblas::algorithm::lastStatus() = gb_step__;                 \
+      return -1.f;                                                    \
+    }                                                                 \
+  } while (0)
+
 // Timer policy shared by the drivers: per-iteration lines need an event
 // synchronisation per level (reference algorithm/bfs.hpp:51-63); with
 // --timing 0 one event pair brackets the whole loop instead.

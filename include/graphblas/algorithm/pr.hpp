@@ -33,16 +33,16 @@ inline Info prNormalize(Matrix<float>* A, float alpha, Descriptor* desc) {
 inline float pr(Vector<float>* p, const Matrix<float>* A, float alpha, float eps,
     Descriptor* desc) {
   Index n;
-  CHECK(A->nrows(&n));
+  GB_ALGO_STEP(A->nrows(&n));
 
-  CHECK(p->clear());
-  CHECK(p->fill(1.f/n));
+  GB_ALGO_STEP(p->clear());
+  GB_ALGO_STEP(p->fill(1.f/n));
 
   Vector<float> p_prev(n);
   Vector<float> p_swap(n);
   Vector<float> r(n);
   Vector<float> r_temp(n);
-  CHECK(r.fill(1.f));
+  GB_ALGO_STEP(r.fill(1.f));
 
   backend::Descriptor& d = desc->descriptor_;
   const bool verbose = (d.timing_ == 1);

@@ -22,24 +22,24 @@ namespace algorithm {
 inline float sssp(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor* desc) {
   const float kInf = std::numeric_limits<float>::max();
   Index n;
-  CHECK(A->nrows(&n));
+  GB_ALGO_STEP(A->nrows(&n));
 
-  CHECK(v->fill(kInf));
-  CHECK(v->setElement(0.f, s));
+  GB_ALGO_STEP(v->fill(kInf));
+  GB_ALGO_STEP(v->setElement(0.f, s));
 
   Vector<float> frontier(n);
   Vector<float> relaxed(n);
   Vector<float> improved(n);
 
   Desc_value mxv_mode;
-  CHECK(desc->get(GrB_MXVMODE, &mxv_mode));
+  GB_ALGO_STEP(desc->get(GrB_MXVMODE, &mxv_mode));
   if (mxv_mode == GrB_PULLONLY) {
-    CHECK(frontier.fill(kInf));
-    CHECK(frontier.setElement(0.f, s));
+    GB_ALGO_STEP(frontier.fill(kInf));
+    GB_ALGO_STEP(frontier.setElement(0.f, s));
   } else {
     std::vector<Index> src_ind(1, s);
     std::vector<float> src_val(1, 0.f);
-    CHECK(frontier.build(&src_ind, &src_val, 1, GrB_NULL));
+    GB_ALGO_STEP(frontier.build(&src_ind, &src_val, 1, GrB_NULL));
   }
 
   backend::Descriptor& d = desc->descriptor_;
@@ -57,13 +57,13 @@ inline float sssp(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor*
     eWiseAdd<float, float, float, float>(v, GrB_NULL, GrB_NULL,
         MinimumPlusSemiring<float>(), v, &relaxed, desc);
 
-    CHECK(desc->toggle(GrB_MASK));
+    GB_ALGO_STEP(desc->toggle(GrB_MASK));
     assign<float, float, float, Index>(&relaxed, &improved, GrB_NULL, kInf,
         GrB_ALL, n, desc);
-    CHECK(desc->toggle(GrB_MASK));
+    GB_ALGO_STEP(desc->toggle(GrB_MASK));
 
-    CHECK(relaxed.swap(&frontier));
-    CHECK(frontier.nvals(&frontier_nvals));
+    GB_ALGO_STEP(relaxed.swap(&frontier));
+    GB_ALGO_STEP(frontier.nvals(&frontier_nvals));
     reduce<float, float>(&succ, GrB_NULL, PlusMonoid<float>(), &improved, desc);
 
     if (verbose) {
