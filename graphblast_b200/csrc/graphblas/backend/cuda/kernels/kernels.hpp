@@ -11,5 +11,6 @@
 #include "graphblas/backend/cuda/kernels/spmv_pull.cuh"
 #include "graphblas/backend/cuda/kernels/spmspv_push.cuh"
 #include "graphblas/backend/cuda/kernels/spgemm_masked.cuh"
+#include "graphblas/backend/cuda/kernels/spgemm_hash.cuh"
 
 #endif  // GRAPHBLAS_BACKEND_CUDA_KERNELS_KERNELS_HPP_

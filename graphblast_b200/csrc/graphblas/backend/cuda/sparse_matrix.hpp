@@ -126,6 +126,9 @@ class SparseMatrix {
   Info printCSR(const char* str) { return printSide(str, hostCsr(), ncols_); }
   Info printCSC(const char* str) { return printSide(str, hostCsc(), nrows_); }
   void dropSpmvTiles();
+  // The entry set stopped being symmetric (tril): from the next upload on the
+  // column-major side owns its index arrays instead of borrowing the CSR's.
+  void dropSymmetry() { if (symmetric_) { releaseDevice(); symmetric_ = false; } }
 
   Side hostCsr() { return Side{h_csrRowPtr_, h_csrColInd_, h_csrVal_, nrows_}; }
   Side hostCsc() { return Side{h_cscColPtr_, h_cscRowInd_, h_cscVal_, ncols_}; }

@@ -48,6 +48,10 @@ Info trilSparse(SparseMatrix<c>* C, SparseMatrix<a>* A, Descriptor* desc) {
   rowptr[A->nrows_] = out;
   A->nvals_ = out;
 
+  // A triangle of a symmetric pattern is not symmetric: the column-major side can
+  // no longer borrow the CSR index arrays (the masked mxm walks mask columns).
+  C->dropSymmetry();
+
   CHECK(C->syncCpu());
   CHECK(C->cpuToGpu());
   return GrB_SUCCESS;

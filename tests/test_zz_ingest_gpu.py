@@ -109,10 +109,15 @@ def test_csr_transpose_values(gb):
 
 @pytest.mark.parametrize("name,directed", [("chesapeake.mtx", 0), ("chesapeake.mtx", 2),
                                            ("test_cc.mtx", 0), ("test_cc.mtx", 2),
-                                           ("test_sgm.mtx", 0), ("test_sgm.mtx", 1)])
+                                           ("test_bc.mtx", 0), ("test_bc.mtx", 1),
+                                           ("test_bc.mtx", 2)])
 def test_matrix_market_path_matches_the_reference_loader(gb, name, directed):
     """gb200_matrix_load_mtx parses on the host and orders / symmetrises / dedups on
-    the device; the CSR must be the reference readMtx + coo2csr's (oracle/_ref)."""
+    the device; the CSR must be the reference readMtx + coo2csr's (oracle/_ref).
+    test_sgm.mtx (nothing but self-loops) is left out: the reference's removeSelfloop
+    (util.hpp:310-322) reads past the end of its vectors when every tuple is dropped,
+    and depending on what the heap holds it returns or dies in vector::resize(-1); the
+    all-loops case is covered in test_ingest_edge_cases."""
     if orc.ref() is None:
         pytest.skip("oracle/_ref not built")
     path = os.path.join(GOLDEN, name)

@@ -46,4 +46,6 @@ python tools/summarize_ncu.py traffic $OUT/prof_bfs_fused.ncu-rep bfs:24:1 bfsFu
 python tools/summarize_ncu.py traffic $OUT/prof_spmv_hub.ncu-rep sssp:22:0 spmvHubKernel
 python tools/summarize_ncu.py traffic $OUT/prof_spmv_hub.ncu-rep pr:22:0 spmvHubKernel
 cp profiles/traffic.json $OUT/traffic.json
+# the reports themselves are too big to travel back (64 MiB limit): keep the text
+rm -f $OUT/*.ncu-rep
 ls -la $OUT | head -40
