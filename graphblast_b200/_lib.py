@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgraphblast_b200.so")
+# GB200_LIB: another build of the same library (kernel-parameter experiments)
+LIB_PATH = os.environ.get("GB200_LIB") or os.path.join(_HERE, "lib", "libgraphblast_b200.so")
 
 _lib = None
 

@@ -26,9 +26,12 @@
 // 10^5 partners and a short list of its own, and one group walking all of them
 // was the whole run time of the first version; the table is rebuilt per item,
 // which costs one pass over a list that is short next to what streams through it.
-// Inside a CTA the warps take partners from a shared counter, a few at a time
-// (partner lists of one owner differ by three orders of magnitude; with a fixed
-// assignment two thirds of the issue slots were barrier waits).
+// Inside a CTA the warps take partners from a shared list one at a time (partner
+// lists of one owner differ by three orders of magnitude; with a fixed assignment
+// two thirds of the issue slots were barrier waits), and the partners are described
+// by all threads at once before any of them is streamed (three dependent loads
+// and, in pass 2, a search per partner — serialised in front of every few lists
+// they cost as much as the streaming).
 #ifndef GRAPHBLAS_BACKEND_CUDA_KERNELS_SPGEMM_HASH_CUH_
 #define GRAPHBLAS_BACKEND_CUDA_KERNELS_SPGEMM_HASH_CUH_
 
@@ -39,15 +42,35 @@ namespace backend {
 
 #define GB_HASH_EMPTY   (-1)
 #define GB_HASH_CAP_S   64       // warp-owned tables: 256 slots, load <= 0.25
-#define GB_HASH_CAP_M   1024     // CTA-owned tables: 4096 slots, load <= 0.25
-#define GB_HASH_SEG_L   8192     // big-CTA tables: 16384 slots, load <= 0.5 per segment
+#define GB_HASH_CAP_M   1024     // CTA-owned tables
 #define GB_HASH_SLOTS_S 256
-#define GB_HASH_SLOTS_M 4096
-#define GB_HASH_SLOTS_L 16384
+#ifndef GB_HASH_SLOTS_M
+#define GB_HASH_SLOTS_M 2048     // load <= 0.5: a probe reads four slots, chains stay short
+#endif
+#ifndef GB_HASH_SLOTS_L
+#define GB_HASH_SLOTS_L 16384    // big-CTA tables
+#endif
+#ifndef GB_HASH_SEG_L
+#define GB_HASH_SEG_L   8192     // keys of a long list that go into the table at a time
+#endif
 #define GB_HASH_NCLASS  3        // S, M, L
 #define GB_HASH_CHUNK_S 256      // partners per work item
 #define GB_HASH_CHUNK_M 1024
+#ifndef GB_HASH_CHUNK_L
 #define GB_HASH_CHUNK_L 2048
+#endif
+#ifndef GB_HASH_UNROLL_M
+#define GB_HASH_UNROLL_M 4       // keys of a partner list in flight per lane
+#endif
+#ifndef GB_HASH_UNROLL_L
+#define GB_HASH_UNROLL_L 8
+#endif
+#ifndef GB_HASH_CTAS_M
+#define GB_HASH_CTAS_M 7         // resident CTAs per SM the launches are sized for
+#endif
+#ifndef GB_HASH_CTAS_L
+#define GB_HASH_CTAS_L 1
+#endif
 
 struct HashItem { Index owner; Index first_partner; };   // index into the M_* arrays
 
@@ -111,13 +134,28 @@ __device__ __forceinline__ unsigned int hashSlot(Index key, int shift) {
   return (static_cast<unsigned int>(key)*0x9E3779B1u) >> shift;
 }
 
+// Shared memory of one group: the table and the item's partner list.
+template <int SLOTS, int CHUNK, typename TV>
+struct __align__(16) HashGroupSmem {
+  Index keys[SLOTS];          // buckets of four slots, filled from the left
+  TV    vals[SLOTS];
+  Index list_beg[CHUNK];      // partners that stream: first entry, length, output slot
+  Index list_len[CHUNK];
+  Index list_out[CHUNK];
+  unsigned int list_size;
+  unsigned int next;          // next partner of the list to be taken by a warp
+};
+
 // One group (a warp when WARP_OWNER, else the CTA) per work item.
 //   T_* : the owners' lists (table side)      P_* : the partners' lists (streamed)
 //   M_* : mask adjacency by owner — CSR rows in pass 1, CSC columns in pass 2
 //   SWAP: pass 2; the table side is B, so products are mul(P value, T value), and
 //         the output slot is looked up in the CSR-ordered mask.
-//   BATCH: partners a warp takes from the item's counter at a time (<= 32).
-template <int CT, bool WARP_OWNER, int SLOTS, int SEG, int CHUNK, int BATCH, bool SWAP,
+// Per item: (A) all threads describe the item's partners — list bounds, whether this
+// owner is in charge of the pair, the output slot — and append the ones that stream
+// to a shared list; (B) the owner's list goes into the table; (C) warps take
+// partners from the list one at a time and stream them through the table.
+template <int CT, bool WARP_OWNER, int SLOTS, int SEG, int CHUNK, int UNROLL, bool SWAP,
           typename c, typename TV, typename PV, typename m,
           typename MulOp, typename AddOp>
 __global__ void __launch_bounds__(CT)
@@ -140,19 +178,14 @@ spgemmHashKernel(c* __restrict__             C_val,
                  AddOp                       add_op,
                  c                           identity,
                  unsigned long long*         list_bytes) {
-  constexpr int GT     = WARP_OWNER ? 32 : CT;          // threads per group
-  constexpr int GROUPS = CT/GT;
+  constexpr int GT = WARP_OWNER ? 32 : CT;              // threads per group
+  typedef HashGroupSmem<SLOTS, CHUNK, TV> Smem;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Index* keys_all = reinterpret_cast<Index*>(smem_raw);
-  TV*    vals_all = reinterpret_cast<TV*>(keys_all + GROUPS*SLOTS);
   __shared__ unsigned int grabbed;
-  __shared__ unsigned int next_batch;
 
   const int lane = threadIdx.x & 31;
-  const int gid  = WARP_OWNER ? (threadIdx.x >> 5) : 0;
   const int gtid = WARP_OWNER ? lane : threadIdx.x;
-  Index* keys = keys_all + gid*SLOTS;
-  TV*    vals = vals_all + gid*SLOTS;
+  Smem& sm = reinterpret_cast<Smem*>(smem_raw)[WARP_OWNER ? (threadIdx.x >> 5) : 0];
   const unsigned int nitems = *item_count;
   unsigned long long scanned = 0;
 
@@ -161,11 +194,11 @@ spgemmHashKernel(c* __restrict__             C_val,
     if (WARP_OWNER) {
       __syncwarp();
       idx = 0;
-      if (lane == 0) idx = atomicAdd(grab, 1u);
+      if (lane == 0) { idx = atomicAdd(grab, 1u); sm.list_size = 0; }
       idx = __shfl_sync(GB_FULL_MASK, idx, 0);
     } else {
-      __syncthreads();                      // previous item's table is done with
-      if (threadIdx.x == 0) grabbed = atomicAdd(grab, 1u);
+      __syncthreads();                      // previous item's table and list are done with
+      if (threadIdx.x == 0) { grabbed = atomicAdd(grab, 1u); sm.list_size = 0; }
       __syncthreads();
       idx = grabbed;
     }
@@ -178,6 +211,27 @@ spgemmHashKernel(c* __restrict__             C_val,
     const Index t_len = __ldg(T_ptr + owner + 1) - t_beg;
     if (gtid == 0) scanned += t_len;
 
+    // (A) the item's partners
+    for (Index q = m_beg + gtid; q < m_end; q += GT) {
+      const Index w     = __ldg(M_ind + q);
+      const Index p_beg = __ldg(P_ptr + w);
+      const Index p_len = __ldg(P_ptr + w + 1) - p_beg;
+      const bool chosen = SWAP ? (p_len < t_len) : (p_len <= t_len);
+      if (!chosen) continue;                // the partner owns this pair
+      const Index out = SWAP ? findSorted(mask_colind, __ldg(mask_rowptr + w),
+                                          __ldg(mask_rowptr + w + 1), owner)
+                             : q;
+      if (p_len > 0 && M_val[q] != 0) {
+        const unsigned int at = atomicAdd(&sm.list_size, 1u);
+        sm.list_beg[at] = p_beg;
+        sm.list_len[at] = p_len;
+        sm.list_out[at] = out;
+        scanned += p_len;
+      } else {
+        C_val[out] = identity;
+      }
+    }
+
     // the owner's list goes through the table SEG keys at a time (one segment
     // unless it is longer than the largest table holds)
     for (Index seg = 0; seg == 0 || seg < t_len; seg += SEG) {
@@ -188,101 +242,92 @@ spgemmHashKernel(c* __restrict__             C_val,
       const int nslots = 1 << lg;
       const int shift  = 32 - lg;
       const unsigned int smask = nslots - 1;
+      const unsigned int bmask = (nslots >> 2) - 1;
+      const int4* buckets = reinterpret_cast<const int4*>(sm.keys);
 
+      // (B)
       if (!WARP_OWNER && seg > 0) __syncthreads();      // previous segment's probes
-      for (int s = gtid; s < nslots; s += GT) keys[s] = GB_HASH_EMPTY;
-      if (!WARP_OWNER && threadIdx.x == 0) next_batch = 0;
+      for (int s = gtid; s < nslots; s += GT) sm.keys[s] = GB_HASH_EMPTY;
+      if (gtid == 0) sm.next = 0;
       if (WARP_OWNER) __syncwarp(); else __syncthreads();
       for (Index p = gtid; p < seg_len; p += GT) {
         const Index key = __ldg(T_ind + t_beg + seg + p);
-        unsigned int s = hashSlot(key, shift);
-        while (atomicCAS(keys + s, GB_HASH_EMPTY, key) != GB_HASH_EMPTY)
+        unsigned int s = hashSlot(key, shift + 2) << 2;      // first slot of the bucket
+        while (atomicCAS(sm.keys + s, GB_HASH_EMPTY, key) != GB_HASH_EMPTY)
           s = (s + 1) & smask;
-        vals[s] = T_val[t_beg + seg + p];
+        sm.vals[s] = T_val[t_beg + seg + p];
       }
       if (WARP_OWNER) __syncwarp(); else __syncthreads();
 
-      // a warp takes BATCH partners at a time: one lane fetches one partner's
-      // description, then the warp streams the selected lists one after the other
-      unsigned int batch = 0;
-      while (true) {
-        if (!WARP_OWNER) {
-          if (lane == 0) batch = atomicAdd(&next_batch, 1u);
-          batch = __shfl_sync(GB_FULL_MASK, batch, 0);
-        }
-        const Index q0 = m_beg + static_cast<Index>(batch)*BATCH;
-        if (q0 >= m_end) break;
-        if (WARP_OWNER) ++batch;
-        const Index q = q0 + lane;
-        Index p_beg = 0, p_len = 0, out = 0;
-        bool  chosen = false, present = false;
-        if (lane < BATCH && q < m_end) {
-          const Index w = __ldg(M_ind + q);
-          p_beg = __ldg(P_ptr + w);
-          p_len = __ldg(P_ptr + w + 1) - p_beg;
-          chosen  = SWAP ? (p_len < t_len) : (p_len <= t_len);
-          present = M_val[q] != 0;
-          if (chosen) {
-            out = SWAP ? findSorted(mask_colind, __ldg(mask_rowptr + w),
-                                    __ldg(mask_rowptr + w + 1), owner)
-                       : q;
-            if (present) scanned += p_len;
-          }
-        }
-        c mine = identity;
-        unsigned int todo = __ballot_sync(GB_FULL_MASK, chosen && present && p_len > 0);
-        // the first 32 keys of the next list are requested before the current
-        // one is probed
-        Index next_key = GB_HASH_EMPTY;
-        int   k_next = todo ? __ffs(todo) - 1 : -1;
-        Index nb = 0, nl = 0;
-        if (k_next >= 0) {
-          nb = __shfl_sync(GB_FULL_MASK, p_beg, k_next);
-          nl = __shfl_sync(GB_FULL_MASK, p_len, k_next);
+      // (C) the first 32 keys of the next list are requested before the current
+      // one is probed
+      const unsigned int nlist = sm.list_size;
+      unsigned int cur = 0;
+      if (lane == 0) cur = atomicAdd(&sm.next, 1u);
+      cur = __shfl_sync(GB_FULL_MASK, cur, 0);
+      Index cb = 0, cl = 0, key = GB_HASH_EMPTY;
+      if (cur < nlist) {
+        cb = sm.list_beg[cur];
+        cl = sm.list_len[cur];
+        if (lane < cl) key = __ldg(P_ind + cb + lane);
+      }
+      while (cur < nlist) {
+        unsigned int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&sm.next, 1u);
+        nxt = __shfl_sync(GB_FULL_MASK, nxt, 0);
+        Index nb = 0, nl = 0, next_key = GB_HASH_EMPTY;
+        if (nxt < nlist) {
+          nb = sm.list_beg[nxt];
+          nl = sm.list_len[nxt];
           if (lane < nl) next_key = __ldg(P_ind + nb + lane);
         }
-        while (k_next >= 0) {
-          const int   k   = k_next;
-          const Index cb  = nb, cl = nl;
-          const Index key = next_key;
-          todo &= todo - 1;
-          k_next = todo ? __ffs(todo) - 1 : -1;
-          next_key = GB_HASH_EMPTY;
-          if (k_next >= 0) {
-            nb = __shfl_sync(GB_FULL_MASK, p_beg, k_next);
-            nl = __shfl_sync(GB_FULL_MASK, p_len, k_next);
-            if (lane < nl) next_key = __ldg(P_ind + nb + lane);
+        c acc = identity;
+        // UNROLL keys of the list in flight per lane
+        for (Index e0 = 0; e0 < cl; e0 += 32*UNROLL) {
+          Index k4[UNROLL];
+          int   hit[UNROLL];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            const Index e = e0 + 32*u + lane;
+            k4[u] = GB_HASH_EMPTY;
+            if (e < cl) k4[u] = (e < 32) ? key : __ldg(P_ind + cb + e);
           }
-          c acc = identity;
-          // four keys of the list in flight per lane
-          for (Index e0 = 0; e0 < cl; e0 += 128) {
-            Index k4[4];
+          // a probe reads a whole bucket of four slots; a bucket fills from the left,
+          // so an empty last slot ends an unsuccessful search
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const Index e = e0 + 32*u + lane;
-              k4[u] = GB_HASH_EMPTY;
-              if (e < cl) k4[u] = (e < 32) ? key : __ldg(P_ind + cb + e);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (k4[u] == GB_HASH_EMPTY) continue;
-              unsigned int s = hashSlot(k4[u], shift);
-              Index at = keys[s];
-              while (at != k4[u] && at != GB_HASH_EMPTY) {
-                s = (s + 1) & smask;
-                at = keys[s];
+          for (int u = 0; u < UNROLL; ++u) {
+            hit[u] = -1;
+            if (k4[u] == GB_HASH_EMPTY) continue;
+            unsigned int bkt = hashSlot(k4[u], shift + 2);
+            while (true) {
+              const int4 w = buckets[bkt];
+              if (w.x == k4[u] || w.y == k4[u] || w.z == k4[u] || w.w == k4[u]) {
+                hit[u] = 4*bkt + ((w.x == k4[u]) ? 0 : (w.y == k4[u]) ? 1
+                                                    : (w.z == k4[u]) ? 2 : 3);
+                break;
               }
-              if (at == k4[u]) {
-                const Index e = e0 + 32*u + lane;
-                if (SWAP) acc = add_op(mul_op(P_val[cb + e], vals[s]), acc);
-                else      acc = add_op(mul_op(vals[s], P_val[cb + e]), acc);
-              }
+              if (w.w == GB_HASH_EMPTY) break;
+              bkt = (bkt + 1) & bmask;
             }
           }
-          acc = warpReduce(acc, add_op);
-          if (lane == k) mine = acc;
+          // the values of the hits are requested together
+          PV pv[UNROLL];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u)
+            if (hit[u] >= 0) pv[u] = P_val[cb + e0 + 32*u + lane];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            if (hit[u] < 0) continue;
+            if (SWAP) acc = add_op(mul_op(pv[u], sm.vals[hit[u]]), acc);
+            else      acc = add_op(mul_op(sm.vals[hit[u]], pv[u]), acc);
+          }
         }
-        if (chosen) C_val[out] = (seg == 0) ? mine : add_op(C_val[out], mine);
+        acc = warpReduce(acc, add_op);
+        if (lane == 0) {
+          const Index out = sm.list_out[cur];
+          C_val[out] = (seg == 0) ? acc : add_op(C_val[out], acc);
+        }
+        cur = nxt; cb = nb; cl = nl; key = next_key;
       }
     }
   }

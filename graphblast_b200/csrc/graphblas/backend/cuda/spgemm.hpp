@@ -28,31 +28,48 @@ Info spgemmHashPass(c* C_val, const HashItem* lists, size_t stride,
     MulOp mul_op, AddOp add_op, c identity, unsigned long long* list_bytes,
     cudaStream_t s) {
   const int sms = runtime().sm_count;
-  const size_t slot_bytes = sizeof(Index) + sizeof(TV);
   {
+    typedef HashGroupSmem<GB_HASH_SLOTS_L, GB_HASH_CHUNK_L, TV> Smem;
     auto kernel = spgemmHashKernel<1024, false, GB_HASH_SLOTS_L, GB_HASH_SEG_L,
-        GB_HASH_CHUNK_L, 4, SWAP, c, TV, PV, m, MulOp, AddOp>;
-    const int bytes = static_cast<int>(GB_HASH_SLOTS_L*slot_bytes);
+        GB_HASH_CHUNK_L, GB_HASH_UNROLL_L, SWAP, c, TV, PV, m, MulOp, AddOp>;
     static bool configured = false;          // per instantiation
     if (!configured) {
       CUDA_CALL(cudaFuncSetAttribute(kernel,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Smem))));
       configured = true;
     }
-    kernel<<<sms, 1024, bytes, s>>>(C_val, lists + 2*stride, counts + 2, grabs + 2,
+    kernel<<<sms*GB_HASH_CTAS_L, 1024, sizeof(Smem), s>>>(C_val, lists + 2*stride, counts + 2,
+        grabs + 2, T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind, M_val,
+        mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
+  }
+  {
+    typedef HashGroupSmem<GB_HASH_SLOTS_M, GB_HASH_CHUNK_M, TV> Smem;
+    auto kernel = spgemmHashKernel<256, false, GB_HASH_SLOTS_M, GB_HASH_CAP_M,
+        GB_HASH_CHUNK_M, GB_HASH_UNROLL_M, SWAP, c, TV, PV, m, MulOp, AddOp>;
+    static bool configured = false;
+    if (!configured) {
+      CUDA_CALL(cudaFuncSetAttribute(kernel,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Smem))));
+      configured = true;
+    }
+    kernel<<<sms*GB_HASH_CTAS_M, 256, sizeof(Smem), s>>>(C_val, lists + stride, counts + 1,
+        grabs + 1, T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind, M_val,
+        mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
+  }
+  {
+    typedef HashGroupSmem<GB_HASH_SLOTS_S, GB_HASH_CHUNK_S, TV> Smem;
+    auto kernel = spgemmHashKernel<256, true, GB_HASH_SLOTS_S, GB_HASH_CAP_S,
+        GB_HASH_CHUNK_S, 2, SWAP, c, TV, PV, m, MulOp, AddOp>;
+    static bool configured = false;
+    if (!configured) {
+      CUDA_CALL(cudaFuncSetAttribute(kernel,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(8*sizeof(Smem))));
+      configured = true;
+    }
+    kernel<<<sms*4, 256, 8*sizeof(Smem), s>>>(C_val, lists, counts, grabs,
         T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind, M_val,
         mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
   }
-  spgemmHashKernel<256, false, GB_HASH_SLOTS_M, GB_HASH_CAP_M, GB_HASH_CHUNK_M, 8, SWAP,
-                   c, TV, PV, m, MulOp, AddOp>
-      <<<sms*6, 256, GB_HASH_SLOTS_M*slot_bytes, s>>>(C_val, lists + stride,
-      counts + 1, grabs + 1, T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind,
-      M_val, mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
-  spgemmHashKernel<256, true, GB_HASH_SLOTS_S, GB_HASH_CAP_S, GB_HASH_CHUNK_S, 32, SWAP,
-                   c, TV, PV, m, MulOp, AddOp>
-      <<<sms*8, 256, 8*GB_HASH_SLOTS_S*slot_bytes, s>>>(C_val, lists,
-      counts, grabs, T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind,
-      M_val, mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
   GB_KERNEL_CHECK();
   return GrB_SUCCESS;
 }
