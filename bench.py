@@ -403,7 +403,7 @@ def workload_config(args, n, nnz, source):
 KINDS = ["spmvMergeKernel / spmvHubKernel (generic pull SpMV)",
          "spmvMaskedOrPullKernel (fused Boolean pull)",
          "spmspvPushKernel (push SpMSpV expand)",
-         "spgemmMaskedKernel (masked dot-product SpGEMM)"]
+         "spgemmHashKernel x6 per call (masked SpGEMM, hash formulation)"]
 
 
 def per_mxv_rates(args, prof, n, nnz, fused=None):
@@ -570,6 +570,11 @@ def main():
         "share_of_step": dom_ms / total_ms if total_ms else 0,
         "traffic": measured_traffic(args, dom),
     }
+    if args.algo == "tc":
+        roofline["note"] = ("achieved = index-list bytes streamed through the tables / "
+                            "time of the six hash launches; about half of them are L2 "
+                            "hits and the kernels are issue-bound (profiles/), so this "
+                            "is not a DRAM fraction")
     if fused_stats is not None:
         roofline["fused_traversal"] = dict(zip(
             ["levels", "entries_inspected_pulling", "pull_levels", "vertices_pushed",

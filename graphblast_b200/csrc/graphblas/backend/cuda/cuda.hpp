@@ -24,6 +24,7 @@
 #include "graphblas/backend/cuda/apply.hpp"
 #include "graphblas/backend/cuda/tri.hpp"
 #include "graphblas/backend/cuda/bfs_fused.hpp"
+#include "graphblas/backend/cuda/loop_steps.hpp"
 #include "graphblas/backend/cuda/operations.hpp"
 
 #endif  // GRAPHBLAS_BACKEND_CUDA_CUDA_HPP_

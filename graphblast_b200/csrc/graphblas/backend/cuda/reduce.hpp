@@ -16,23 +16,12 @@
 namespace graphblas {
 namespace backend {
 
-template <typename T, typename U,
-          typename BinaryOpT, typename MonoidT>
-Info reduceCommon(T* val, BinaryOpT accum, MonoidT op, const U* d_val, Index nvals,
-    Descriptor* desc) {
-  if (nvals == 0) {
-    *val = op.identity();
-    return GrB_SUCCESS;
-  }
-  const int grid = gridFor(nvals, GB_REDUCE_NT, 4);
-  T* partials = reinterpret_cast<T*>(desc->scratch(GB_SCRATCH_BLOCKSUM,
-      (static_cast<size_t>(grid) + 1)*sizeof(T)));
+// Second launch of a reduction: one CTA folds the per-CTA partials; a 32-bit
+// result is posted to the host mailbox (no stream synchronisation).
+template <typename T, typename MonoidT>
+Info reduceFold(T* val, MonoidT op, T* partials, int grid) {
   T* d_out = partials + grid;
   cudaStream_t s = gbStream();
-  reducePartialKernel<<<grid, GB_REDUCE_NT, 0, s>>>(partials, d_val, nvals, op,
-      static_cast<T>(op.identity()));
-  GB_KERNEL_CHECK();
-  // a 32-bit result is posted to the host mailbox (no stream synchronisation)
   static const bool use_mail = getEnv("GB200_MAILBOX", 1) != 0;
   const bool mail = use_mail && sizeof(T) == 4;
   const unsigned long long ticket = mail ? runtime().mailTicket() : 0ull;
@@ -57,6 +46,30 @@ Info reduceCommon(T* val, BinaryOpT accum, MonoidT op, const U* d_val, Index nva
   }
   *val = runtime().fetch(d_out);
   return GrB_SUCCESS;
+}
+
+// Grid of the first launch and the scratch its partials (+ the result cell) live in.
+template <typename T>
+T* reducePartials(Index nvals, Descriptor* desc, int* grid) {
+  *grid = gridFor(nvals, GB_REDUCE_NT, 4);
+  return reinterpret_cast<T*>(desc->scratch(GB_SCRATCH_BLOCKSUM,
+      (static_cast<size_t>(*grid) + 1)*sizeof(T)));
+}
+
+template <typename T, typename U,
+          typename BinaryOpT, typename MonoidT>
+Info reduceCommon(T* val, BinaryOpT accum, MonoidT op, const U* d_val, Index nvals,
+    Descriptor* desc) {
+  if (nvals == 0) {
+    *val = op.identity();
+    return GrB_SUCCESS;
+  }
+  int grid;
+  T* partials = reducePartials<T>(nvals, desc, &grid);
+  reducePartialKernel<<<grid, GB_REDUCE_NT, 0, gbStream()>>>(partials, d_val, nvals, op,
+      static_cast<T>(op.identity()));
+  GB_KERNEL_CHECK();
+  return reduceFold(val, op, partials, grid);
 }
 
 // Dense vector

@@ -41,6 +41,7 @@ Info spgemmHashPass(c* C_val, const HashItem* lists, size_t stride,
     kernel<<<sms*GB_HASH_CTAS_L, 1024, sizeof(Smem), s>>>(C_val, lists + 2*stride, counts + 2,
         grabs + 2, T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind, M_val,
         mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
+    GB_KERNEL_CHECK();
   }
   {
     typedef HashGroupSmem<GB_HASH_SLOTS_M, GB_HASH_CHUNK_M, TV> Smem;
@@ -55,6 +56,7 @@ Info spgemmHashPass(c* C_val, const HashItem* lists, size_t stride,
     kernel<<<sms*GB_HASH_CTAS_M, 256, sizeof(Smem), s>>>(C_val, lists + stride, counts + 1,
         grabs + 1, T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind, M_val,
         mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
+    GB_KERNEL_CHECK();
   }
   {
     typedef HashGroupSmem<GB_HASH_SLOTS_S, GB_HASH_CHUNK_S, TV> Smem;
@@ -69,8 +71,8 @@ Info spgemmHashPass(c* C_val, const HashItem* lists, size_t stride,
     kernel<<<sms*4, 256, 8*sizeof(Smem), s>>>(C_val, lists, counts, grabs,
         T_ptr, T_ind, T_val, P_ptr, P_ind, P_val, M_ptr, M_ind, M_val,
         mask_rowptr, mask_colind, mul_op, add_op, identity, list_bytes);
+    GB_KERNEL_CHECK();
   }
-  GB_KERNEL_CHECK();
   return GrB_SUCCESS;
 }
 
@@ -157,6 +159,7 @@ Info spgemmMasked(SparseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum,
           CUDA_CALL(cudaMemsetAsync(cells, 0, 32*sizeof(unsigned int), s));
           spgemmHashClassifyKernel<<<gridFor(A_nrows, 256), 256, 0, s>>>(A_csrRowPtr,
               sparse_mask->d_csrRowPtr_, A_nrows, false, lists, stride, cells);
+          GB_KERNEL_CHECK();
           spgemmHashClassifyKernel<<<gridFor(B_ncols, 256), 256, 0, s>>>(B_cscColPtr,
               sparse_mask->d_cscColPtr_, B_ncols, true,
               lists + GB_HASH_NCLASS*stride, stride, cells + 4);

@@ -43,6 +43,7 @@ inline float pr(Vector<float>* p, const Matrix<float>* A, float alpha, float eps
   Vector<float> r(n);
   Vector<float> r_temp(n);
   GB_ALGO_STEP(r.fill(1.f));
+  GB_ALGO_STEP(p_prev.fill(0.f));      // dense from the start: it trades places with p
 
   backend::Descriptor& d = desc->descriptor_;
   const bool verbose = (d.timing_ == 1);
@@ -52,16 +53,23 @@ inline float pr(Vector<float>* p, const Matrix<float>* A, float alpha, float eps
   clock.begin();
 
   for (iter = 1; error > eps && iter <= d.max_niter_; ++iter) {
-    p_prev = *p;
+    // p_prev = p ; p = p_prev (+.*) A + (1-alpha)/n ; error = |p - p_prev|_2.
+    // Dense vectors (always, here): the old ranks change hands by a swap and the
+    // update + difference + square + sum are one pass (backend loop_steps.hpp);
+    // otherwise the reference's operations (algorithm/pr.hpp:49-66).
+    GB_ALGO_STEP(p->swap(&p_prev));
     vxm<float, float, float, float>(&p_swap, GrB_NULL, GrB_NULL,
         PlusMultipliesSemiring<float>(), &p_prev, A, desc);
-    eWiseAdd<float, float, float, float>(p, GrB_NULL, GrB_NULL,
-        PlusMultipliesSemiring<float>(), &p_swap, (1.f - alpha)/n, desc);
-    eWiseMult<float, float, float, float>(&r, GrB_NULL, GrB_NULL,
-        PlusMinusSemiring<float>(), p, &p_prev, desc);
-    eWiseAdd<float, float, float, float>(&r_temp, GrB_NULL, GrB_NULL,
-        MultipliesMultipliesSemiring<float>(), &r, &r, desc);
-    reduce<float, float>(&error, GrB_NULL, PlusMonoid<float>(), &r_temp, desc);
+    if (backend::prUpdateStep(&p->vector_, &p_swap.vector_, &p_prev.vector_,
+                              (1.f - alpha)/n, &error, &desc->descriptor_) != GrB_SUCCESS) {
+      eWiseAdd<float, float, float, float>(p, GrB_NULL, GrB_NULL,
+          PlusMultipliesSemiring<float>(), &p_swap, (1.f - alpha)/n, desc);
+      eWiseMult<float, float, float, float>(&r, GrB_NULL, GrB_NULL,
+          PlusMinusSemiring<float>(), p, &p_prev, desc);
+      eWiseAdd<float, float, float, float>(&r_temp, GrB_NULL, GrB_NULL,
+          MultipliesMultipliesSemiring<float>(), &r, &r, desc);
+      reduce<float, float>(&error, GrB_NULL, PlusMonoid<float>(), &r_temp, desc);
+    }
     error = sqrt(error);
 
     if (verbose) {

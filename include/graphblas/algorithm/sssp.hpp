@@ -52,19 +52,28 @@ inline float sssp(Vector<float>* v, const Matrix<float>* A, Index s, Descriptor*
   for (int round = 1; round <= d.max_niter_; ++round) {
     vxm<float, float, float, float>(&relaxed, GrB_NULL, GrB_NULL,
         MinimumPlusSemiring<float>(), &frontier, A, desc);
-    eWiseAdd<float, float, float, float>(&improved, GrB_NULL, GrB_NULL,
-        CustomLessPlusSemiring<float>(), &relaxed, v, desc);
-    eWiseAdd<float, float, float, float>(v, GrB_NULL, GrB_NULL,
-        MinimumPlusSemiring<float>(), v, &relaxed, desc);
+    // improved = relaxed < v ; v = min(v, relaxed) ; relaxed<!improved> = inf ;
+    // succ = |improved| — one pass when everything is dense (backend loop_steps.hpp),
+    // else the reference's four operations (algorithm/sssp.hpp:60-75).
+    if (backend::ssspRelaxStep(&v->vector_, &relaxed.vector_, kInf, &succ,
+                               &desc->descriptor_) == GrB_SUCCESS) {
+      GB_ALGO_STEP(relaxed.swap(&frontier));
+      GB_ALGO_STEP(frontier.nvals(&frontier_nvals));
+    } else {
+      eWiseAdd<float, float, float, float>(&improved, GrB_NULL, GrB_NULL,
+          CustomLessPlusSemiring<float>(), &relaxed, v, desc);
+      eWiseAdd<float, float, float, float>(v, GrB_NULL, GrB_NULL,
+          MinimumPlusSemiring<float>(), v, &relaxed, desc);
 
-    GB_ALGO_STEP(desc->toggle(GrB_MASK));
-    assign<float, float, float, Index>(&relaxed, &improved, GrB_NULL, kInf,
-        GrB_ALL, n, desc);
-    GB_ALGO_STEP(desc->toggle(GrB_MASK));
+      GB_ALGO_STEP(desc->toggle(GrB_MASK));
+      assign<float, float, float, Index>(&relaxed, &improved, GrB_NULL, kInf,
+          GrB_ALL, n, desc);
+      GB_ALGO_STEP(desc->toggle(GrB_MASK));
 
-    GB_ALGO_STEP(relaxed.swap(&frontier));
-    GB_ALGO_STEP(frontier.nvals(&frontier_nvals));
-    reduce<float, float>(&succ, GrB_NULL, PlusMonoid<float>(), &improved, desc);
+      GB_ALGO_STEP(relaxed.swap(&frontier));
+      GB_ALGO_STEP(frontier.nvals(&frontier_nvals));
+      reduce<float, float>(&succ, GrB_NULL, PlusMonoid<float>(), &improved, desc);
+    }
 
     if (verbose) {
       float ms = clock.lap();
