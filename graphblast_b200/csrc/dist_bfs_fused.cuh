@@ -32,6 +32,10 @@
 
 #include <cooperative_groups.h>
 
+// CTA shape of the distributed traversal kernel (validated at 2 and 8 GPUs with this
+// shape; the single-GPU kernel chooses its own, kernels/bfs_fused.cuh)
+#define GBX_BFS_NT 1024
+
 namespace gbx {
 
 struct BfsDistArgs {
@@ -79,11 +83,11 @@ __device__ __forceinline__ unsigned long long distNow() {
 } while (0)
 
 template <int MINB>
-__global__ void __launch_bounds__(GB_BFS_NT, MINB)
+__global__ void __launch_bounds__(GBX_BFS_NT, MINB)
 bfsFusedDistKernel(BfsDistArgs a) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
-  __shared__ int s_red[GB_BFS_NT/32];
+  __shared__ int s_red[GBX_BFS_NT/32];
   __shared__ unsigned long long s_total;
   __shared__ bool s_failed;
 
@@ -241,7 +245,7 @@ bfsFusedDistKernel(BfsDistArgs a) {
         }
       }
     }
-    const int block_found = blockSum<GB_BFS_NT>(found_here, s_red);
+    const int block_found = blockSum<GBX_BFS_NT>(found_here, s_red);
     if (threadIdx.x == 0 && block_found)
       atomicAdd(found_cell, static_cast<unsigned long long>(block_found));
     grid.sync();
@@ -356,17 +360,8 @@ int gb200_dist_bfs_fused(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
 
   // first-neighbour summary of the local rows (same cache as the Boolean pull)
   const int fw = 0;
-  if (S.d_pull_first_[fw] == NULL || S.pull_first_key_[fw] != S.d_csrRowPtr_ ||
-      S.pull_first_nvals_[fw] != S.nvals_) {
-    if (S.d_pull_first_[fw] != NULL) gbFree(S.d_pull_first_[fw]);
-    S.d_pull_first_[fw] = reinterpret_cast<Index*>(
-        gbMalloc((static_cast<size_t>(S.nrows_) + 1)*sizeof(Index)));
-    pullFirstNeighbourKernel<<<gridFor(S.nrows_, 256, 8), 256, 0, s>>>(
-        S.d_pull_first_[fw], S.d_csrRowPtr_, S.d_csrColInd_, S.nrows_);
-    GB_KERNEL_CHECK();
-    S.pull_first_key_[fw] = S.d_csrRowPtr_;
-    S.pull_first_nvals_[fw] = S.nvals_;
-  }
+  const Index* first = backend::pullFirstNeighbours(&S, fw, S.d_csrRowPtr_, S.d_csrColInd_,
+                                                    S.nrows_);
 
   const size_t w_lo = x->word_off[x->rank];
   const size_t nw = x->word_off[x->rank + 1] - w_lo;
@@ -375,7 +370,7 @@ int gb200_dist_bfs_fused(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
       own_bytes + 1024 + GB_BFS_HEAVY_CAP*sizeof(Index)));
   gbx::BfsDistArgs a;
   a.pull_ptr = S.d_csrRowPtr_;  a.pull_ind = S.d_csrColInd_;
-  a.pull_first = S.d_pull_first_[fw];
+  a.pull_first = first;
   a.push_ptr = S.d_cscColPtr_;  a.push_ind = S.d_cscRowInd_;
   a.n = static_cast<Index>(n);  a.nl = nl;  a.source = static_cast<Index>(source);
   a.lo = static_cast<long long>(w_lo)*32;
@@ -404,14 +399,14 @@ int gb200_dist_bfs_fused(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
   static int resident = 0;
   if (resident == 0) {
     int per_sm = 0;
-    CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GB_BFS_NT, 0));
+    CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GBX_BFS_NT, 0));
     resident = per_sm*runtime().sm_count;
     if (resident < 1) return rc(GrB_PANIC);
   }
   void* params[] = { &a };
   profiler().begin(GB_PROF_PULL_BOOL, s);
   CUDA_CALL(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(resident),
-      dim3(GB_BFS_NT), params, 0, s));
+      dim3(GBX_BFS_NT), params, 0, s));
   GB_KERNEL_CHECK();
   profiler().end(GB_PROF_PULL_BOOL, s, 0.0);
   v->f->vector_.dense_.touched();

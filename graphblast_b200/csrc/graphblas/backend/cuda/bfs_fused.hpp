@@ -58,17 +58,7 @@ Info bfsFused(Vector<float>* v, const Matrix<a>* A, Index s, Descriptor* desc, i
 
   // first-neighbour summary of the pulled structure (shared with the Boolean pull)
   const int fw = 1;                                   // vxm pulls over the CSC
-  if (S->d_pull_first_[fw] == NULL || S->pull_first_key_[fw] != S->d_cscColPtr_ ||
-      S->pull_first_nvals_[fw] != S->nvals_) {
-    if (S->d_pull_first_[fw] != NULL) gbFree(S->d_pull_first_[fw]);
-    S->d_pull_first_[fw] = reinterpret_cast<Index*>(
-        gbMalloc((static_cast<size_t>(n) + 1)*sizeof(Index)));
-    pullFirstNeighbourKernel<<<gridFor(n, 256, 8), 256, 0, stream>>>(
-        S->d_pull_first_[fw], S->d_cscColPtr_, S->d_cscRowInd_, n);
-    GB_KERNEL_CHECK();
-    S->pull_first_key_[fw] = S->d_cscColPtr_;
-    S->pull_first_nvals_[fw] = S->nvals_;
-  }
+  const Index* first = pullFirstNeighbours(S, fw, S->d_cscColPtr_, S->d_cscRowInd_, n);
 
   const size_t nwords = (static_cast<size_t>(n) + 31)/32;
   const size_t words_bytes = ((nwords*sizeof(unsigned int) + 255)/256)*256;
@@ -77,7 +67,8 @@ Info bfsFused(Vector<float>* v, const Matrix<a>* A, Index s, Descriptor* desc, i
   BfsFusedArgs args;
   args.push_ptr = S->d_csrRowPtr_;  args.push_ind = S->d_csrColInd_;
   args.pull_ptr = S->d_cscColPtr_;  args.pull_ind = S->d_cscRowInd_;
-  args.pull_first = S->d_pull_first_[fw];
+  args.pull_first = first;
+  args.pull_empty = pullEmptyRowBits(first, n);
   args.n = n;
   args.source = s;
   args.max_levels = desc->max_niter_;
@@ -95,7 +86,7 @@ Info bfsFused(Vector<float>* v, const Matrix<a>* A, Index s, Descriptor* desc, i
 
   static const int minb = getEnv("GB200_BFS_MINB", 2);
   static int resident = 0;               // CTAs that fit at once (cooperative launch)
-  void (*kernel)(BfsFusedArgs) = (minb >= 2) ? bfsFusedKernel<2> : bfsFusedKernel<1>;
+  void (*kernel)(BfsFusedArgs) = (minb >= 2) ? bfsFusedKernel<GB_BFS_MINB> : bfsFusedKernel<1>;
   if (resident == 0) {
     int per_sm = 0;
     CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
@@ -119,6 +110,22 @@ Info bfsFused(Vector<float>* v, const Matrix<a>* A, Index s, Descriptor* desc, i
     GB_KERNEL_CHECK();
   }
   v->dense_.touched();
+  static const int trace = getEnv("GB200_BFS_TRACE", 0);
+  if (trace) {                           // per-level times of this traversal
+    unsigned long long cells[32];
+    CUDA_CALL(cudaMemcpyAsync(cells, args.counters, sizeof(cells), cudaMemcpyDeviceToHost,
+        stream));
+    runtime().sync();
+    const int levels = static_cast<int>(cells[6] < 15 ? cells[6] : 15);
+    fprintf(stderr, "bfs trace: set-up %.1fus",
+            1e-3*static_cast<double>((cells[12] >> 1) - cells[28]));
+    for (int l = 1; l <= levels; ++l)
+      fprintf(stderr, " L%d %s %.1fus", l, (cells[12 + l] & 1ull) ? "pull" : "push",
+              1e-3*static_cast<double>((cells[12 + l] >> 1) - (cells[12 + l - 1] >> 1)));
+    fprintf(stderr, " | L2 CTA0: scan %.1fus walk %.1fus parked %llu\n",
+            1e-3*static_cast<double>(cells[29] - (cells[13] >> 1)),
+            1e-3*static_cast<double>(cells[30] - cells[29]), cells[31]);
+  }
   if (depth != NULL) {
     const unsigned long long levels = runtime().fetch(args.counters + 6);
     *depth = static_cast<int>(levels);

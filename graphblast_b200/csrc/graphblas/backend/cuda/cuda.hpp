@@ -14,6 +14,7 @@
 #include "graphblas/backend/cuda/sparse_matrix.hpp"
 #include "graphblas/backend/cuda/dense_matrix.hpp"
 #include "graphblas/backend/cuda/matrix.hpp"
+#include "graphblas/backend/cuda/pull_summary.hpp"
 #include "graphblas/backend/cuda/spmv.hpp"
 #include "graphblas/backend/cuda/spmspv.hpp"
 #include "graphblas/backend/cuda/spgemm.hpp"

@@ -38,17 +38,25 @@
 namespace graphblas {
 namespace backend {
 
+// CTA shape, measured on RMAT-24: 768 x 2 per SM 0.275 ms, 512 x 3 0.281, 1024 x 2
+// 0.305 (32 registers: the pull loop spills), 1024 x 1 0.297 (no spills, half the
+// warps: the first pull level is latency-bound and takes 40 % longer).
 #ifndef GB_BFS_NT
-#define GB_BFS_NT     1024
+#define GB_BFS_NT     768
+#endif
+#ifndef GB_BFS_MINB
+#define GB_BFS_MINB   2               // resident CTAs per SM the register budget allows
 #endif
 #define GB_BFS_HEAVY  2048            // adjacency longer than this: grid-wide expansion
 #define GB_BFS_HEAVY_CAP 4096         // heavy vertices per level kept in the list
+#define GB_BFS_PARK   4096            // rows a CTA parks for its walking phase per pull level
 
 struct BfsFusedArgs {
   // structure: rows to expand when pushing, rows to inspect when pulling
   const Index* push_ptr;   const Index* push_ind;     // out-neighbours of a vertex
   const Index* pull_ptr;   const Index* pull_ind;     // in-neighbours of a vertex
   const Index* pull_first;                            // first-neighbour summary of pull_*
+  const unsigned int* pull_empty;                     // bitmap of rows without in-neighbours
   Index n;
   Index source;
   int   max_levels;
@@ -65,9 +73,17 @@ struct BfsFusedArgs {
                                   // is zeroed during level L-1, filled during L and
                                   // read after L's barrier, when slow threads may still
                                   // be reading the cell of L-1),
-                                  // [6] levels executed, [7..11] work counters (out)
+                                  // [6] levels executed, [7..11] work counters (out),
+                                  // [12..27] time at the end of the set-up and of every
+                                  // level (ns << 1 | pulled), for GB200_BFS_TRACE
   Index*        heavy;            // [GB_BFS_HEAVY_CAP]
 };
+
+__device__ __forceinline__ unsigned long long bfsClockNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ bool bfsClaim(unsigned int* visited, Index vtx) {
   const unsigned int bit = 1u << (vtx & 31);
@@ -84,6 +100,9 @@ bfsFusedKernel(BfsFusedArgs a) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ int s_red[GB_BFS_NT/32];
+  __shared__ int s_parked;                 // rows waiting in s_park (pull levels)
+  __shared__ Index s_park[GB_BFS_PARK];
+  if (threadIdx.x == 0) s_parked = 0;
 
   const Index n = a.n;
   const Index nwords = (n + 31) >> 5;
@@ -93,15 +112,20 @@ bfsFusedKernel(BfsFusedArgs a) {
   const Index gwarp = gtid >> 5;
   const Index gwarps = gthreads >> 5;
 
+  if (gtid == 0) a.counters[28] = bfsClockNs();
   // ---- level 0: clear the state, seed the source ---------------------------------
   for (Index i = gtid; i < n; i += gthreads)
     a.levels[i] = (i == a.source) ? 1.f : 0.f;
   for (Index w = gtid; w < nwords; w += gthreads) {
     const unsigned int seed = (w == (a.source >> 5)) ? (1u << (a.source & 31)) : 0u;
-    a.visited[0][w] = seed; a.visited[1][w] = 0u; a.frontier[w] = seed; a.next[w] = 0u;
+    // rows nothing points at count as visited from the start: no level can discover
+    // them, and the pull levels would look at them every time
+    a.visited[0][w] = seed | a.pull_empty[w];
+    a.visited[1][w] = 0u; a.frontier[w] = seed; a.next[w] = 0u;
   }
   if (gtid < 12) a.counters[gtid] = 0ull;
   grid.sync();
+  if (gtid == 0) a.counters[12] = bfsClockNs() << 1;          // [12..27]: level clock
 
   unsigned int* vis = a.visited[0];       // visited as of the level's start
   unsigned int* vis_other = a.visited[1];
@@ -212,6 +236,16 @@ bfsFusedKernel(BfsFusedArgs a) {
           const Index word = g*4 + j;
           mword[j] = (word < nwords) ? vis[word] : 0xffffffffu;
         }
+        if ((mword[0] & mword[1] & mword[2] & mword[3]) == 0xffffffffu) {
+          // nothing left to discover in these 128 rows (the common case after the
+          // first pull level): only the bitmaps move on
+          if (lane < 4 && g*4 + lane < nwords) {
+            N[g*4 + lane] = 0u;
+            vis_other[g*4 + lane] = 0xffffffffu;
+            F[g*4 + lane] = 0u;
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const Index row = (g*4 + j)*32 + lane;
@@ -229,7 +263,20 @@ bfsFusedKernel(BfsFusedArgs a) {
           const Index word = g*4 + j;
           const Index row = word*32 + lane;
           bool found = (pword[j] >> (f[j] & 31)) & 1u;
-          if (f[j] >= 0 && !found) {           // more entries: walk them, early exit
+          // more entries and the first one not visited: the row has to be walked.
+          // Few lanes of a warp are in that position and a walk is a chain of
+          // dependent loads, so the rows are parked in a CTA-wide list and walked by
+          // all threads after the scan (inline only when the list is full).
+          bool walk = (f[j] >= 0 && !found);
+          const unsigned int walkers = __ballot_sync(GB_FULL_MASK, walk);
+          if (walkers != 0u) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_parked, __popc(walkers));
+            base = __shfl_sync(GB_FULL_MASK, base, 0);
+            const int slot = base + __popc(walkers & ((1u << lane) - 1u));
+            if (walk && slot < GB_BFS_PARK) { s_park[slot] = row; walk = false; }
+          }
+          if (walk) {
             Index k = __ldg(a.pull_ptr + row) + 1;
             const Index end = __ldg(a.pull_ptr + row + 1);
             for (; k < end; ++k) {
@@ -250,12 +297,53 @@ bfsFusedKernel(BfsFusedArgs a) {
           found_here += found ? 1 : 0;
         }
       }
+      // the parked rows, one per thread at a time
+      __syncthreads();
+      if (gtid == 0 && level == 2) { a.counters[29] = bfsClockNs(); a.counters[31] = s_parked; }
+      const int parked = (s_parked < GB_BFS_PARK) ? s_parked : GB_BFS_PARK;
+      for (int i = threadIdx.x; i < parked; i += GB_BFS_NT) {
+        const Index row = s_park[i];
+        Index k = __ldg(a.pull_ptr + row) + 1;
+        const Index end = __ldg(a.pull_ptr + row + 1);
+        bool found = false;
+        // four entries per step: their bitmap words are fetched together, then
+        // examined in list order (the count stops at the first visited one)
+        while (k < end && !found) {
+          Index col[4];
+          unsigned int word[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            col[u] = (k + u < end) ? __ldg(a.pull_ind + k + u) : static_cast<Index>(-1);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            word[u] = (col[u] >= 0) ? vis[col[u] >> 5] : 0u;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (found || col[u] < 0) continue;
+            ++inspected;
+            found = (word[u] >> (col[u] & 31)) & 1u;
+          }
+          k += 4;
+        }
+        if (found) {
+          const unsigned int bit = 1u << (row & 31);
+          atomicOr(N + (row >> 5), bit);
+          atomicOr(vis_other + (row >> 5), bit);
+          a.levels[row] = next_level;
+          ++found_here;
+        }
+      }
+      __syncthreads();
+      if (gtid == 0 && level == 2) a.counters[30] = bfsClockNs();
+      if (threadIdx.x == 0) s_parked = 0;
     }
     // ---- frontier size of the next level ------------------------------------------
     const int block_found = blockSum<GB_BFS_NT>(found_here, s_red);
     if (threadIdx.x == 0 && block_found)
       atomicAdd(count_cell, static_cast<unsigned long long>(block_found));
     grid.sync();
+    if (gtid == 0 && level < 16)
+      a.counters[12 + level] = (bfsClockNs() << 1) | (dense ? 1ull : 0ull);
     fcount = *reinterpret_cast<volatile unsigned long long*>(count_cell);
     if (dense) { unsigned int* t = vis; vis = vis_other; vis_other = t; }
     { unsigned int* t = F; F = N; N = t; }

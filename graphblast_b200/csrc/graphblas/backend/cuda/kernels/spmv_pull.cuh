@@ -413,6 +413,22 @@ __global__ void pullFirstNeighbourKernel(Index* __restrict__ first,
   }
 }
 
+// bits[w] bit b = row 32w+b has no entry (first == -1); rows past the end read 0.
+// A traversal marks these rows visited up front: nothing can discover them, and a
+// third of an R-MAT's rows would otherwise be looked at on every pull level.
+__global__ void pullEmptyRowBitsKernel(unsigned int* __restrict__ bits,
+                                       const Index* __restrict__ first, Index nrows) {
+  const int lane = threadIdx.x & 31;
+  Index row = blockIdx.x*blockDim.x + threadIdx.x;
+  const Index stride = gridDim.x*blockDim.x;
+  const Index padded = ((nrows + 31) >> 5) << 5;
+  for (; row < padded; row += stride) {            // whole warps: padded is a multiple of 32
+    const bool empty = row < nrows && __ldg(first + row) == static_cast<Index>(-1);
+    const unsigned int word = __ballot_sync(GB_FULL_MASK, empty);
+    if (lane == 0) bits[row >> 5] = word;
+  }
+}
+
 template <bool UseScmp, bool UseEarlyExit, bool UseOpReuse, typename W>
 __global__ void __launch_bounds__(GB_PULL_NT)
 spmvMaskedOrPullBitsKernel(W* __restrict__                  w,

@@ -174,19 +174,8 @@ Info spmv(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT o
         // First-neighbour summary of this structure, computed once per matrix.
         SparseMatrix<a>* A_f = const_cast<SparseMatrix<a>*>(A);
         const int fw = use_tran ? 1 : 0;
-        if (A_f->d_pull_first_[fw] == NULL ||
-            A_f->pull_first_key_[fw] != A_csrRowPtr ||
-            A_f->pull_first_nvals_[fw] != A->nvals_) {
-          if (A_f->d_pull_first_[fw] != NULL) gbFree(A_f->d_pull_first_[fw]);
-          A_f->d_pull_first_[fw] = reinterpret_cast<Index*>(
-              gbMalloc((static_cast<size_t>(A_nrows) + 1)*sizeof(Index)));
-          pullFirstNeighbourKernel<<<gridFor(A_nrows, 256, 8), 256, 0, s>>>(
-              A_f->d_pull_first_[fw], A_csrRowPtr, A_csrColInd, A_nrows);
-          GB_KERNEL_CHECK();
-          A_f->pull_first_key_[fw]   = A_csrRowPtr;
-          A_f->pull_first_nvals_[fw] = A->nvals_;
-        }
-        const Index* A_first = A_f->d_pull_first_[fw];
+        const Index* A_first = pullFirstNeighbours(A_f, fw, A_csrRowPtr, A_csrColInd,
+                                                   A_nrows);
         // The 0/1 result is published through the bitmap shadow only; the value
         // array is written when somebody asks for it (DenseVector::materialize).
         static const bool eager = getEnv("GB200_EAGER_VALUES", 0) != 0;

@@ -1,7 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for mb in 4 3 2; do
-GB200_BFS_MINB=$mb timeout 300 python bench.py --algo bfs --scale 24 --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('minb $mb ms/step %.3f launches %d'%(d['ms_per_step'], d['gpu_launches']))"
-done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:bfsFusedKernel -s 3 -c 1 -o gpurun_out/bfs_prof -f python bench.py --algo bfs --scale 24 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bfs_ncu.log 2>&1
-tail -3 gpurun_out/bfs_ncu.log
+run() {  # name lib env
+  GB200_LIB=$PWD/build/variants/$2 $3 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2> gpurun_out/bfsv_$1.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$1: bfs ms/step %.4f' % d['ms_per_step'])"
+  GB200_BFS_TRACE=1 GB200_LIB=$PWD/build/variants/$2 $3 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "bfs trace" | tail -1
+}
+run nt1024x2 nt1024x2.so env
+run nt768x2 nt768x2.so env
+run nt512x3 nt512x3.so env
+run nt1024x1 nt1024x1.so "env GB200_BFS_MINB=1"
