@@ -42,6 +42,7 @@ struct BfsDistArgs {
   // local (nl x n) matrix: CSR rows = owned vertices with their in-neighbours
   // (global ids); CSC = per global vertex its owned out-neighbours (local ids)
   const Index* pull_ptr;  const Index* pull_ind;  const Index* pull_first;
+  const unsigned int* pull_empty;    // owned rows without in-neighbours (bitmap)
   const Index* push_ptr;  const Index* push_ind;
   Index n, nl, source;
   long long lo;                      // first owned vertex (multiple of 32)
@@ -113,7 +114,10 @@ bfsFusedDistKernel(BfsDistArgs a) {
       reinterpret_cast<unsigned int*>(local + a.off_visited[1])};
   for (Index w = gtid; w < total_words; w += gthreads) {
     const unsigned int seed = (w == (a.source >> 5)) ? (1u << (a.source & 31)) : 0u;
-    vis_copy[1][w] = seed;
+    // owned rows nothing points at count as visited from the start (no level can
+    // discover them; the owner's merged words carry the bits to the other ranks)
+    const bool own = w >= word_lo && w < word_lo + nw;
+    vis_copy[1][w] = seed | (own ? a.pull_empty[w - word_lo] : 0u);
     a.seed[w] = seed;
   }
   for (Index w = gtid; w < nw + 8; w += gthreads) a.next_own[w] = 0u;
@@ -211,6 +215,10 @@ bfsFusedDistKernel(BfsDistArgs a) {
         for (int j = 0; j < 4; ++j) {
           const Index word = g*4 + j;
           mword[j] = (word < nw) ? __ldcg(vis + word_lo + word) : 0xffffffffu;
+        }
+        if ((mword[0] & mword[1] & mword[2] & mword[3]) == 0xffffffffu) {
+          if (lane < 4 && g*4 + lane < nw) a.next_own[g*4 + lane] = 0u;   // nothing to find
+          continue;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -371,6 +379,7 @@ int gb200_dist_bfs_fused(gb200_xchg_t x, gb200_vector_t v, gb200_matrix_t M,
   gbx::BfsDistArgs a;
   a.pull_ptr = S.d_csrRowPtr_;  a.pull_ind = S.d_csrColInd_;
   a.pull_first = first;
+  a.pull_empty = backend::pullEmptyRowBits(first, S.nrows_);
   a.push_ptr = S.d_cscColPtr_;  a.push_ind = S.d_cscRowInd_;
   a.n = static_cast<Index>(n);  a.nl = nl;  a.source = static_cast<Index>(source);
   a.lo = static_cast<long long>(w_lo)*32;

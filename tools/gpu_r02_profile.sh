@@ -23,6 +23,7 @@ run_bench sssp_rmat22 --algo sssp --steps 10 --warmup 3
 run_bench sssp_rmat24_pushpull --algo sssp --scale 24 --mxvmode 0 --steps 5 --warmup 3
 run_bench pr_rmat22 --algo pr --steps 5 --warmup 3
 run_bench tc_rmat22 --algo tc --steps 3 --warmup 3
+run_bench tc_rmat20 --algo tc --scale 20 --steps 5 --warmup 3
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/r02_bench_reference_arm_bfs_rmat24.json 2>/dev/null
 timeout 600 python bench.py --impl reference --algo sssp --steps 2 --warmup 1 > $OUT/r02_bench_reference_arm_sssp_rmat22.json 2>/dev/null
 # launch lists (cold cache, serialised: shares only)
@@ -32,6 +33,9 @@ python tools/summarize_ncu.py launches $OUT/r02_launches_bfs_rmat24.csv > $OUT/r
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv \
     --log-file $OUT/r02_launches_sssp_rmat22.csv python bench.py --algo sssp --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 python tools/summarize_ncu.py launches $OUT/r02_launches_sssp_rmat22.csv > $OUT/r02_launches_sssp_rmat22.txt 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file $OUT/r02_launches_tc_rmat22.csv python bench.py --algo tc --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+python tools/summarize_ncu.py launches $OUT/r02_launches_tc_rmat22.csv > $OUT/r02_launches_tc_rmat22.txt 2>&1
 # full captures of the dominant kernels
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bfsFusedKernel -s 2 -c 1 -f \
     -o $OUT/prof_bfs_fused python bench.py --steps 2 --warmup 2 --no-cpu-baseline > /dev/null 2>&1
@@ -39,7 +43,7 @@ python tools/summarize_ncu.py full $OUT/prof_bfs_fused.ncu-rep > $OUT/r02_ncu_bf
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmvHubKernel -s 2 -c 1 -f \
     -o $OUT/prof_spmv_hub python bench.py --algo sssp --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 python tools/summarize_ncu.py full $OUT/prof_spmv_hub.ncu-rep > $OUT/r02_ncu_spmv_hub_rmat22.txt 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:spgemmMasked -s 2 -c 2 -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spgemmHashKernel -s 6 -c 3 -f \
     -o $OUT/prof_tc python bench.py --algo tc --scale 20 --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 python tools/summarize_ncu.py full $OUT/prof_tc.ncu-rep > $OUT/r02_ncu_tc_rmat20.txt 2>&1
 python tools/summarize_ncu.py traffic $OUT/prof_bfs_fused.ncu-rep bfs:24:1 bfsFusedKernel
