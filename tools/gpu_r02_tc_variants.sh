@@ -1,5 +1,11 @@
 #!/bin/bash
 # kernel-parameter variants of the hash SpGEMM (build/variants/*.so), RMAT-22
+# (profiles/r02_tc_hash_variants.txt).  Built on the CPU box with the library's nvcc
+# line plus, e.g.:
+#   v1: -DGB_HASH_SLOTS_M=2048 -DGB_HASH_CTAS_M=7 -DGB_HASH_SLOTS_L=8192 -DGB_HASH_SEG_L=4096 -DGB_HASH_CTAS_L=2 -DGB_HASH_UNROLL_L=8
+#   v2: -DGB_HASH_SLOTS_M=2048 -DGB_HASH_CTAS_M=7 -DGB_HASH_UNROLL_L=8            (shipped defaults)
+#   v3: v1 with -DGB_HASH_SEG_L=6144 -DGB_HASH_UNROLL_L=4 -DGB_HASH_CHUNK_L=1024 -DGB_HASH_UNROLL_M=2
+# and selected at run time through GB200_LIB.
 mkdir -p gpurun_out
 for v in $(ls build/variants/*.so); do
   name=$(basename $v .so)
