@@ -237,53 +237,13 @@ int gb200_desc_toggle(gb200_desc_t desc, int field) {
 
 int gb200_desc_set_knob(gb200_desc_t desc, const char* name, double value) {
   if (desc == NULL || name == NULL) return rc(graphblas::GrB_NULL_POINTER);
-  graphblas::backend::Descriptor& d = desc->desc.descriptor_;
-  std::string k(name);
-  if (k == "mxvmode") {
-    d.mxvmode_ = static_cast<int>(value);
-    graphblas::Desc_value m = d.mxvmode_ == 0 ? graphblas::GrB_PUSHPULL :
-                              d.mxvmode_ == 1 ? graphblas::GrB_PUSHONLY :
-                                                graphblas::GrB_PULLONLY;
-    if (d.mxvmode_ < 0 || d.mxvmode_ > 2)
-      return rc(graphblas::GrB_INVALID_VALUE);
-    return rc(d.set(graphblas::GrB_MXVMODE, m));
-  }
-  if (k == "switchpoint") { d.switchpoint_ = static_cast<float>(value); return 0; }
-  if (k == "struconly")   { d.struconly_ = value != 0; return 0; }
-  if (k == "opreuse")     { d.opreuse_ = value != 0; return 0; }
-  if (k == "earlyexit")   { d.earlyexit_ = value != 0; return 0; }
-  if (k == "fusedmask")   { d.fusedmask_ = value != 0; return 0; }
-  if (k == "sort")        { d.sort_ = value != 0; return 0; }
-  if (k == "dirinfo")     { d.dirinfo_ = value != 0; return 0; }
-  if (k == "debug")       { d.debug_ = value != 0; return 0; }
-  if (k == "timing")      { d.timing_ = static_cast<int>(value); return 0; }
-  if (k == "max_niter")   { d.max_niter_ = static_cast<int>(value); return 0; }
-  if (k == "memusage")    { d.memusage_ = static_cast<float>(value); return 0; }
-  if (k == "nthread")     { d.nthread_ = static_cast<int>(value); return 0; }
-  return rc(graphblas::GrB_INVALID_VALUE);
+  return rc(desc->desc.descriptor_.setKnob(name, value));
 }
 
 int gb200_desc_get_knob(gb200_desc_t desc, const char* name, double* value) {
   if (desc == NULL || name == NULL || value == NULL)
     return rc(graphblas::GrB_NULL_POINTER);
-  graphblas::backend::Descriptor& d = desc->desc.descriptor_;
-  std::string k(name);
-  if      (k == "mxvmode")     *value = d.mxvmode_;
-  else if (k == "switchpoint") *value = d.switchpoint_;
-  else if (k == "struconly")   *value = d.struconly_;
-  else if (k == "opreuse")     *value = d.opreuse_;
-  else if (k == "earlyexit")   *value = d.earlyexit_;
-  else if (k == "fusedmask")   *value = d.fusedmask_;
-  else if (k == "sort")        *value = d.sort_;
-  else if (k == "dirinfo")     *value = d.dirinfo_;
-  else if (k == "debug")       *value = d.debug_;
-  else if (k == "timing")      *value = d.timing_;
-  else if (k == "max_niter")   *value = d.max_niter_;
-  else if (k == "memusage")    *value = d.memusage_;
-  else if (k == "nthread")     *value = d.nthread_;
-  else if (k == "lastmxv")     *value = static_cast<int>(d.lastmxv_);
-  else return rc(graphblas::GrB_INVALID_VALUE);
-  return 0;
+  return rc(desc->desc.descriptor_.getKnob(name, value));
 }
 
 // ---- Matrix -----------------------------------------------------------------

@@ -3,7 +3,8 @@
 //
 // Replaces reference graphblas/backend/cuda/descriptor.hpp:14-287.  Same field
 // table (desc_[GrB_NDESCFIELD]), same toggle() rule (:141-154), same knob names
-// and accessors, same loadArgs() mapping from po::variables_map (:207-287).
+// and accessors; loadArgs() (:207-287), setKnob() and getKnob() are three functors
+// over one enumeration of the knobs.
 // Data members the reference drivers reach through `#define private public`
 // keep their names: max_niter_, timing_, lastmxv_, debug_
 // (reference algorithm/bfs.hpp:46,54,56).
@@ -42,59 +43,145 @@ enum ScratchSlot {
   GB_SCRATCH_NSLOTS
 };
 
+// One visitor enumerates the command-line knobs (name -> member); loading a
+// variables_map, setting a knob by name and reading one back are three functors
+// over it.  Names and types are the drivers' (reference util.hpp:39-132).
 class Descriptor {
  public:
-  Descriptor() : desc_{ GrB_DEFAULT, GrB_DEFAULT, GrB_DEFAULT, GrB_DEFAULT,
-    GrB_FIXEDROW, GrB_32, GrB_32, GrB_128, GrB_PUSHPULL, GrB_16, GrB_CUDA},
-    d_buffer_(NULL), d_buffer_size_(0), d_temp_(NULL), d_temp_size_(0),
-    ta_(0), tb_(0), mode_(""), split_(0),
-    enable_split_(0), niter_(0), max_niter_(0), directed_(0), timing_(0),
-    transpose_(0), mtxinfo_(0), verbose_(0), mxvmode_(0),
-    lastmxv_(GrB_PUSHONLY), switchpoint_(0), dirinfo_(0), struconly_(0),
-    opreuse_(0), memusage_(0), endbit_(0), sort_(0), atomic_(0),
-    earlyexit_(0), fusedmask_(0), nthread_(0), ndevice_(0), debug_(0),
-    memory_(0), acc_elems_(0), acc_identity_bits_(0), acc_elem_bytes_(0),
-    acc_valid_(false), bits_words_(0), bits_valid_(false),
-    lookback_epoch_(0), lookback_ticket_(0) {
-    for (int i = 0; i < GB_SCRATCH_NSLOTS; ++i) {
-      slot_ptr_[i]  = NULL;
-      slot_size_[i] = 0;
-    }
+  Descriptor() {
+    static const Desc_value kDefaults[GrB_NDESCFIELD] = {
+        GrB_DEFAULT, GrB_DEFAULT, GrB_DEFAULT, GrB_DEFAULT,     // mask, outp, inp0, inp1
+        GrB_FIXEDROW, GrB_32, GrB_32, GrB_128, GrB_PUSHPULL, GrB_16, GrB_CUDA};
+    for (int f = 0; f < GrB_NDESCFIELD; ++f) desc_[f] = kDefaults[f];
+    for (int i = 0; i < GB_SCRATCH_NSLOTS; ++i) { slot_ptr_[i] = NULL; slot_size_[i] = 0; }
+  }
+  ~Descriptor() {
+    cudaFree(d_buffer_);                      // cudaFree(NULL) is a no-op
+    cudaFree(d_temp_);
+    for (int i = 0; i < GB_SCRATCH_NSLOTS; ++i) cudaFree(slot_ptr_[i]);
   }
 
-  ~Descriptor();
+  // ---- field table -----------------------------------------------------------------
+  Info set(Desc_field field, Desc_value value) { desc_[field] = value; return GrB_SUCCESS; }
+  Info get(Desc_field field, Desc_value* value) const {
+    *value = desc_[field];
+    return GrB_SUCCESS;
+  }
+  // MASK, OUTP, INP0, INP1 flip between GrB_DEFAULT and their one other value
+  // (GrB_SCMP, GrB_REPLACE, GrB_TRAN, GrB_TRAN); other fields are left alone
+  // (reference :141-154).
+  Info toggle(Desc_field field) {
+    static const Desc_value kOther[4] = {GrB_SCMP, GrB_REPLACE, GrB_TRAN, GrB_TRAN};
+    const int f = static_cast<int>(field);
+    if (f < 4) desc_[f] = (desc_[f] == GrB_DEFAULT) ? kOther[f] : GrB_DEFAULT;
+    return GrB_SUCCESS;
+  }
 
-  // C API Methods
-  Info set(Desc_field field, Desc_value  value);
-  Info get(Desc_field field, Desc_value* value) const;
+  // ---- knobs -------------------------------------------------------------------------
+  template <typename Visitor>
+  void eachKnob(Visitor&& knob) {
+    knob("ta", ta_);                   knob("tb", tb_);
+    knob("mode", mode_);               knob("split", split_);
+    knob("niter", niter_);             knob("max_niter", max_niter_);
+    knob("directed", directed_);       knob("timing", timing_);
+    knob("transpose", transpose_);     knob("mtxinfo", mtxinfo_);
+    knob("verbose", verbose_);         knob("mxvmode", mxvmode_);
+    knob("switchpoint", switchpoint_); knob("dirinfo", dirinfo_);
+    knob("struconly", struconly_);     knob("opreuse", opreuse_);
+    knob("memusage", memusage_);       knob("endbit", endbit_);
+    knob("sort", sort_);               knob("atomic", atomic_);
+    knob("earlyexit", earlyexit_);     knob("fusedmask", fusedmask_);
+    knob("nthread", nthread_);         knob("ndevice", ndevice_);
+    knob("debug", debug_);             knob("memory", memory_);
+  }
+  // Fields that follow a knob: GrB_MXVMODE from mxvmode, GrB_NT from nthread.
+  Info settleMode() {
+    static const Desc_value kModes[3] = {GrB_PUSHPULL, GrB_PUSHONLY, GrB_PULLONLY};
+    if (mxvmode_ < 0 || mxvmode_ > 2) {
+      std::cout << "Error: incorrect mxvmode selection!\n";
+      return GrB_INVALID_VALUE;
+    }
+    desc_[GrB_MXVMODE] = kModes[mxvmode_];
+    return GrB_SUCCESS;
+  }
+  Info settleThreads() {
+    static const struct { int threads; Desc_value value; } kThreads[] = {
+        {32, GrB_32}, {64, GrB_64}, {128, GrB_128}, {256, GrB_256}, {512, GrB_512},
+        {1024, GrB_1024}};
+    for (const auto& t : kThreads)
+      if (t.threads == nthread_) { desc_[GrB_NT] = t.value; return GrB_SUCCESS; }
+    std::cout << "Error: incorrect nthread selection!\n";
+    return GrB_INVALID_VALUE;
+  }
+  // All knobs from the drivers' command line (reference :207-287); a wrong mode or
+  // thread count is reported and otherwise ignored, as there.
+  Info loadArgs(const po::variables_map& vm) {
+    eachKnob(FromArgs{vm});
+    settleMode();
+    settleThreads();
+    return GrB_SUCCESS;
+  }
+  // One knob by name (C ABI); numbers arrive as double.
+  Info setKnob(const std::string& name, double value) {
+    if (name == "mxvmode" && (value < 0 || value > 2)) return GrB_INVALID_VALUE;
+    ByName pick{name, value, false, false};
+    eachKnob(pick);
+    if (!pick.found) return GrB_INVALID_VALUE;
+    if (name == "mxvmode") return settleMode();
+    if (name == "nthread") settleThreads();
+    return GrB_SUCCESS;
+  }
+  Info getKnob(const std::string& name, double* value) {
+    if (name == "lastmxv") { *value = static_cast<int>(lastmxv_); return GrB_SUCCESS; }
+    ByName pick{name, 0.0, true, false};
+    eachKnob(pick);
+    if (!pick.found) return GrB_INVALID_VALUE;
+    *value = pick.value;
+    return GrB_SUCCESS;
+  }
 
-  // Useful methods
-  Info toggle(Desc_field field);
-  Info loadArgs(const po::variables_map& vm);
+  bool  debug()       { return debug_; }
+  bool  memory()      { return memory_; }
+  bool  split()       { return split_ && enable_split_; }
+  bool  struconly()   { return struconly_; }
+  bool  opreuse()     { return opreuse_; }
+  bool  earlyexit()   { return earlyexit_; }
+  bool  fusedmask()   { return fusedmask_; }
+  bool  dirinfo()     { return dirinfo_; }
+  bool  endbit()      { return endbit_; }
+  bool  sort()        { return sort_; }
+  bool  atomic()      { return atomic_; }
+  float switchpoint() { return switchpoint_; }
+  float memusage()    { return memusage_; }
 
-  inline bool debug()  { return debug_;  }
-  inline bool memory() { return memory_; }
+  // ---- legacy two-buffer scratch (reference :156-192), for callers that name
+  // "buffer" / "temp" -------------------------------------------------------------------
+  Info resize(size_t target, std::string field) {
+    const bool temp = (field == "temp");
+    void*&  block = temp ? d_temp_ : d_buffer_;
+    size_t& size  = temp ? d_temp_size_ : d_buffer_size_;
+    if (target <= size) return GrB_SUCCESS;
+    void* grown = NULL;
+    CUDA_CALL(cudaMalloc(&grown, target));
+    if (block != NULL) {                      // contents survive a resize
+      CUDA_CALL(cudaMemcpyAsync(grown, block, size, cudaMemcpyDeviceToDevice, gbStream()));
+      CUDA_CALL(cudaStreamSynchronize(gbStream()));
+      CUDA_CALL(cudaFree(block));
+    }
+    block = grown;
+    size  = target;
+    return GrB_SUCCESS;
+  }
+  Info clear(std::string field) {
+    const bool temp = (field == "temp");
+    if (!temp && field != "buffer") return GrB_SUCCESS;
+    void* block = temp ? d_temp_ : d_buffer_;
+    if (block != NULL)
+      CUDA_CALL(cudaMemsetAsync(block, 0, temp ? d_temp_size_ : d_buffer_size_, gbStream()));
+    return GrB_SUCCESS;
+  }
 
-  inline bool struconly()    { return struconly_; }
-  inline bool split()        { return split_ && enable_split_; }
-  inline bool dirinfo()      { return dirinfo_; }
-  inline bool earlyexit()    { return earlyexit_; }
-  inline bool opreuse()      { return opreuse_; }
-  inline bool endbit()       { return endbit_; }
-  inline bool sort()         { return sort_; }
-  inline bool fusedmask()    { return fusedmask_; }
-  inline bool atomic()       { return atomic_; }
-  inline float switchpoint() { return switchpoint_; }
-  inline float memusage()    { return memusage_; }
-
- public:  // (private in the reference; its drivers `#define private public`)
-  // Legacy two-buffer interface (reference descriptor.hpp:156-192), kept for
-  // callers that size "buffer"/"temp" by name.
-  Info resize(size_t target, std::string field);
-  Info clear(std::string field);
-
- public:
-  // Arena interface used by this backend's operations.
+  // ---- arenas used by this backend's operations --------------------------------------
   void* scratch(ScratchSlot slot, size_t bytes) {
     if (bytes > slot_size_[slot]) {
       if (slot_ptr_[slot] != NULL) {
@@ -127,8 +214,8 @@ class Descriptor {
     return reinterpret_cast<unsigned long long*>(
         slot_ptr_[GB_SCRATCH_LOOKBACK]);
   }
-  unsigned int       lookback_epoch_;
-  unsigned long long lookback_ticket_;
+  unsigned int       lookback_epoch_ = 0;
+  unsigned long long lookback_ticket_ = 0;
 
   // Device counters: 64 x 8-byte cells, zero when first handed out.  Cell 2 is
   // the "finished CTAs" counter of the compaction's count pass, which leaves it
@@ -142,179 +229,63 @@ class Descriptor {
         slot_ptr_[GB_SCRATCH_COUNTERS]);
   }
 
- public:  // (private in the reference; its drivers `#define private public`)
+  // ---- data (private in the reference; its drivers `#define private public` and
+  // reach max_niter_, timing_, lastmxv_, debug_) ----------------------------------------
   Desc_value desc_[GrB_NDESCFIELD];
 
-  void*       d_buffer_;      // legacy scratch
-  size_t      d_buffer_size_;
-  void*       d_temp_;        // legacy cub scratch
-  size_t      d_temp_size_;
+  void*  d_buffer_ = NULL;   size_t d_buffer_size_ = 0;     // legacy scratch
+  void*  d_temp_ = NULL;     size_t d_temp_size_ = 0;       // legacy cub scratch
+  void*  slot_ptr_[GB_SCRATCH_NSLOTS];
+  size_t slot_size_[GB_SCRATCH_NSLOTS];
 
-  void*       slot_ptr_[GB_SCRATCH_NSLOTS];
-  size_t      slot_size_[GB_SCRATCH_NSLOTS];
-
-  // Algorithm specific params
-  int         ta_;
-  int         tb_;
+  // knobs, in the order of eachKnob
+  int ta_ = 0, tb_ = 0;                       // algorithm specific
   std::string mode_;
-  bool        split_;
-  bool        enable_split_;
-
-  // General params
-  int         niter_;
-  int         max_niter_;
-  int         directed_;
-  int         timing_;
-  bool        transpose_;
-  bool        mtxinfo_;
-  bool        verbose_;
-
-  // mxv params
-  int         mxvmode_;
-  Desc_value  lastmxv_;
-  float       switchpoint_;
-  bool        dirinfo_;
-  bool        struconly_;
-  bool        opreuse_;
-
-  // mxv (spmspv/push) params
-  float       memusage_;
-  bool        endbit_;
-  bool        sort_;
-  bool        atomic_;
-
-  // mxv (spmv/pull) params
-  bool        earlyexit_;
-  bool        fusedmask_;
-
-  // GPU params
-  int         nthread_;
-  int         ndevice_;
-  bool        debug_;
-  bool        memory_;
+  bool split_ = false, enable_split_ = false;
+  int niter_ = 0, max_niter_ = 0, directed_ = 0, timing_ = 0;      // general
+  bool transpose_ = false, mtxinfo_ = false, verbose_ = false;
+  int mxvmode_ = 0;                           // mxv
+  Desc_value lastmxv_ = GrB_PUSHONLY;         // direction the last mxv took
+  float switchpoint_ = 0.f;
+  bool dirinfo_ = false, struconly_ = false, opreuse_ = false;
+  float memusage_ = 0.f;                      // push
+  bool endbit_ = false, sort_ = false, atomic_ = false;
+  bool earlyexit_ = false, fusedmask_ = false;                     // pull
+  int nthread_ = 0, ndevice_ = 0;             // device
+  bool debug_ = false, memory_ = false;
 
   // State of the push accumulator arena: which identity it is filled with.
-  size_t      acc_elems_;
-  unsigned    acc_identity_bits_;
-  size_t      acc_elem_bytes_;
-  bool        acc_valid_;
-  size_t      bits_words_;
-  bool        bits_valid_;
+  size_t   acc_elems_ = 0;
+  unsigned acc_identity_bits_ = 0;
+  size_t   acc_elem_bytes_ = 0;
+  bool     acc_valid_ = false;
+  size_t   bits_words_ = 0;
+  bool     bits_valid_ = false;
+
+ private:
+  struct FromArgs {                           // knob <- vm[name]
+    const po::variables_map& vm;
+    template <typename Field>
+    void operator()(const char* name, Field& field) const {
+      field = vm[name].template as<Field>();
+    }
+  };
+  struct ByName {                             // one knob <-> a double
+    const std::string& name;
+    double value;
+    bool   reading;
+    bool   found;
+    void operator()(const char*, std::string&) {}
+    template <typename Field>
+    void operator()(const char* knob_name, Field& field) {
+      if (name != knob_name) return;
+      found = true;
+      if (reading) value = static_cast<double>(field);
+      else         field = static_cast<Field>(value);
+    }
+  };
 };
 
-inline Descriptor::~Descriptor() {
-  if (d_buffer_ != NULL) cudaFree(d_buffer_);
-  if (d_temp_   != NULL) cudaFree(d_temp_);
-  for (int i = 0; i < GB_SCRATCH_NSLOTS; ++i)
-    if (slot_ptr_[i] != NULL) cudaFree(slot_ptr_[i]);
-}
-
-inline Info Descriptor::set(Desc_field field, Desc_value value) {
-  desc_[field] = value;
-  return GrB_SUCCESS;
-}
-
-inline Info Descriptor::get(Desc_field field, Desc_value* value) const {
-  *value = desc_[field];
-  return GrB_SUCCESS;
-}
-
-// Fields 0..3 (MASK, OUTP, INP0, INP1) flip between GrB_DEFAULT and their one
-// non-default value; the enum is laid out so that value == field for the first
-// three (GrB_SCMP=0, GrB_REPLACE=1, GrB_TRAN=2) and INP1 also maps to GrB_TRAN.
-inline Info Descriptor::toggle(Desc_field field) {
-  int idx = static_cast<int>(field);
-  if (idx >= 4) return GrB_SUCCESS;
-  if (desc_[field] != GrB_DEFAULT)
-    desc_[field] = GrB_DEFAULT;
-  else
-    desc_[field] = (idx == 3) ? GrB_TRAN : static_cast<Desc_value>(idx);
-  return GrB_SUCCESS;
-}
-
-inline Info Descriptor::resize(size_t target, std::string field) {
-  void**  ptr  = (field == "temp") ? &d_temp_      : &d_buffer_;
-  size_t* size = (field == "temp") ? &d_temp_size_ : &d_buffer_size_;
-  if (target > *size) {
-    void* fresh = NULL;
-    CUDA_CALL(cudaMalloc(&fresh, target));
-    if (*ptr != NULL) {
-      CUDA_CALL(cudaMemcpyAsync(fresh, *ptr, *size, cudaMemcpyDeviceToDevice, gbStream()));
-      CUDA_CALL(cudaStreamSynchronize(gbStream()));
-      CUDA_CALL(cudaFree(*ptr));
-    }
-    *ptr  = fresh;
-    *size = target;
-  }
-  return GrB_SUCCESS;
-}
-
-inline Info Descriptor::clear(std::string field) {
-  if (field == "buffer" && d_buffer_ != NULL)
-    CUDA_CALL(cudaMemsetAsync(d_buffer_, 0, d_buffer_size_, gbStream()));
-  else if (field == "temp" && d_temp_ != NULL)
-    CUDA_CALL(cudaMemsetAsync(d_temp_, 0, d_temp_size_, gbStream()));
-  return GrB_SUCCESS;
-}
-
-inline Info Descriptor::loadArgs(const po::variables_map& vm) {
-  // Algorithm specific params
-  ta_             = vm["ta"            ].as<int>();
-  tb_             = vm["tb"            ].as<int>();
-  mode_           = vm["mode"          ].as<std::string>();
-  split_          = vm["split"         ].as<bool>();
-
-  // General params
-  niter_          = vm["niter"         ].as<int>();
-  max_niter_      = vm["max_niter"     ].as<int>();
-  directed_       = vm["directed"      ].as<int>();
-  timing_         = vm["timing"        ].as<int>();
-  transpose_      = vm["transpose"     ].as<bool>();
-  mtxinfo_        = vm["mtxinfo"       ].as<bool>();
-  verbose_        = vm["verbose"       ].as<bool>();
-
-  // mxv params
-  mxvmode_        = vm["mxvmode"       ].as<int>();
-  switchpoint_    = vm["switchpoint"   ].as<float>();
-  dirinfo_        = vm["dirinfo"       ].as<bool>();
-  struconly_      = vm["struconly"     ].as<bool>();
-  opreuse_        = vm["opreuse"       ].as<bool>();
-
-  // mxv (spmspv/push) params
-  memusage_       = vm["memusage"      ].as<float>();
-  endbit_         = vm["endbit"        ].as<bool>();
-  sort_           = vm["sort"          ].as<bool>();
-  atomic_         = vm["atomic"        ].as<bool>();
-
-  // mxv (spmv/pull) params
-  earlyexit_      = vm["earlyexit"     ].as<bool>();
-  fusedmask_      = vm["fusedmask"     ].as<bool>();
-
-  // GPU params
-  nthread_        = vm["nthread"       ].as<int>();
-  ndevice_        = vm["ndevice"       ].as<int>();
-  debug_          = vm["debug"         ].as<bool>();
-  memory_         = vm["memory"        ].as<bool>();
-
-  switch (mxvmode_) {
-    case 0: CHECK(set(GrB_MXVMODE, GrB_PUSHPULL)); break;
-    case 1: CHECK(set(GrB_MXVMODE, GrB_PUSHONLY)); break;
-    case 2: CHECK(set(GrB_MXVMODE, GrB_PULLONLY)); break;
-    default: std::cout << "Error: incorrect mxvmode selection!\n";
-  }
-
-  switch (nthread_) {
-    case 32:   CHECK(set(GrB_NT, GrB_32));   break;
-    case 64:   CHECK(set(GrB_NT, GrB_64));   break;
-    case 128:  CHECK(set(GrB_NT, GrB_128));  break;
-    case 256:  CHECK(set(GrB_NT, GrB_256));  break;
-    case 512:  CHECK(set(GrB_NT, GrB_512));  break;
-    case 1024: CHECK(set(GrB_NT, GrB_1024)); break;
-    default: std::cout << "Error: incorrect nthread selection!\n";
-  }
-
-  return GrB_SUCCESS;
-}
 }  // namespace backend
 }  // namespace graphblas
 

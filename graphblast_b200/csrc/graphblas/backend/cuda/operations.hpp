@@ -401,8 +401,8 @@ Info reduce(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
     const Matrix<a>* A, Descriptor* desc) {
   CHECK(w->setStorage(GrB_DENSE));
   if (mask != NULL) return notBuilt("masked reduce");
-  if (A->isSparse()) return reduceInner(&w->dense_, mask, accum, op, &A->sparse_, desc);
-  if (A->isDense())  return reduceInner(&w->dense_, mask, accum, op, &A->dense_, desc);
+  if (A->isSparse()) return reduceRows(&w->dense_, op, &A->sparse_, desc);
+  if (A->isDense())  return notBuilt("row reduce of a dense matrix");
   return GrB_UNINITIALIZED_OBJECT;
 }
 
@@ -410,9 +410,12 @@ Info reduce(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
 template <typename T, typename U,
           typename BinaryOpT, typename MonoidT>
 Info reduce(T* val, BinaryOpT accum, MonoidT op, const Vector<U>* u, Descriptor* desc) {
-  if (u->vec_type_ == GrB_SPARSE)     CHECK(reduceInner(val, accum, op, &u->sparse_, desc));
-  else if (u->vec_type_ == GrB_DENSE) CHECK(reduceInner(val, accum, op, &u->dense_, desc));
-  else return GrB_UNINITIALIZED_OBJECT;
+  if (u->vec_type_ == GrB_SPARSE)
+    CHECK(reduceStored(val, accum, op, &u->sparse_, desc));
+  else if (u->vec_type_ == GrB_DENSE)
+    CHECK(reduceDense(val, accum, op, const_cast<DenseVector<U>*>(&u->dense_), desc));
+  else
+    return GrB_UNINITIALIZED_OBJECT;
   if (desc->debug()) std::cout << "reduce output: " << *val << std::endl;
   return GrB_SUCCESS;
 }
@@ -421,7 +424,7 @@ Info reduce(T* val, BinaryOpT accum, MonoidT op, const Vector<U>* u, Descriptor*
 template <typename T, typename a,
           typename BinaryOpT,     typename MonoidT>
 Info reduce(T* val, BinaryOpT accum, MonoidT op, const Matrix<a>* A, Descriptor* desc) {
-  if (A->isSparse()) return reduceInner(val, accum, op, &A->sparse_, desc);
+  if (A->isSparse()) return reduceStored(val, accum, op, &A->sparse_, desc);
   if (A->isDense())  return notBuilt("reduce of a dense matrix to a scalar");
   return GrB_UNINITIALIZED_OBJECT;
 }

@@ -72,81 +72,58 @@ Info reduceCommon(T* val, BinaryOpT accum, MonoidT op, const U* d_val, Index nva
   return reduceFold(val, op, partials, grid);
 }
 
-// Dense vector
-template <typename T, typename U,
-          typename BinaryOpT, typename MonoidT>
-Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const DenseVector<U>* u,
-    Descriptor* desc) {
-  DenseVector<U>* u_t = const_cast<DenseVector<U>*>(u);
-  // plus-like monoid over a 0/1 vector == number of ones.
-  if (u_t->zero_one_ && op(3, 5) == 8 && op.identity() == static_cast<T>(0)) {
-    Index count;
-    CHECK(u_t->computeNnz(&count, static_cast<U>(0), desc));
-    *val = static_cast<T>(count);
+// ---- container -> scalar ------------------------------------------------------------
+// What a reduction folds: the stored values of a container and how many there are.
+namespace reduce_detail {
+template <typename U> const U* stored(const SparseVector<U>* x) { return x->d_val_; }
+template <typename U> const U* stored(const SparseMatrix<U>* x) { return x->d_csrVal_; }
+template <typename U> Index    count(const SparseVector<U>* x)  { return x->nvals_; }
+template <typename U> Index    count(const SparseMatrix<U>* x)  { return x->nvals_; }
+}  // namespace reduce_detail
+
+// Sparse vector or sparse matrix: in struct-only mode the result is the entry count
+// (reference :71-72, :87-88), else the fold of the stored values.
+template <typename T, typename Container, typename BinaryOpT, typename MonoidT>
+Info reduceStored(T* val, BinaryOpT accum, MonoidT op, const Container* x,
+                  Descriptor* desc) {
+  if (desc->struconly()) {
+    *val = reduce_detail::count(x);
     return GrB_SUCCESS;
   }
-  CHECK(u_t->materialize());
+  return reduceCommon(val, accum, op, reduce_detail::stored(x), reduce_detail::count(x),
+                      desc);
+}
+
+// Dense vector.  A 0/1 vector left by the fused Boolean pull carries its count: a
+// plus-like monoid over it is that count, no pass over the values.
+template <typename T, typename U, typename BinaryOpT, typename MonoidT>
+Info reduceDense(T* val, BinaryOpT accum, MonoidT op, DenseVector<U>* u,
+                 Descriptor* desc) {
+  const bool counts_ones = u->zero_one_ && op(3, 5) == 8 &&
+                           op.identity() == static_cast<T>(0);
+  if (counts_ones) {
+    Index ones;
+    CHECK(u->computeNnz(&ones, static_cast<U>(0), desc));
+    *val = static_cast<T>(ones);
+    return GrB_SUCCESS;
+  }
+  CHECK(u->materialize());
   return reduceCommon(val, accum, op, u->d_val_, u->nvals_, desc);
 }
 
-// Sparse vector
-template <typename T, typename U,
-          typename BinaryOpT, typename MonoidT>
-Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const SparseVector<U>* u,
-    Descriptor* desc) {
-  if (desc->struconly())
-    *val = u->nvals_;
-  else
-    return reduceCommon(val, accum, op, u->d_val_, u->nvals_, desc);
-  return GrB_SUCCESS;
-}
-
-// Sparse matrix -> scalar
-template <typename T, typename a,
-          typename BinaryOpT, typename MonoidT>
-Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const SparseMatrix<a>* A,
-    Descriptor* desc) {
-  if (desc->struconly())
-    *val = A->nvals_;
-  else
-    return reduceCommon(val, accum, op, A->d_csrVal_, A->nvals_, desc);
-  return GrB_SUCCESS;
-}
-
-// Dense matrix -> vector: placeholder, as in the reference (:94-104)
-template <typename W, typename a, typename M,
-          typename BinaryOpT,     typename MonoidT>
-Info reduceInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
-    const DenseMatrix<a>* A, Descriptor* desc) {
-  std::cout << "Error: Dense reduce matrix-to-vector not implemented yet!\n";
-  return GrB_SUCCESS;
-}
-
-// Sparse matrix rows -> dense vector
-template <typename W, typename a, typename M,
-          typename BinaryOpT,     typename MonoidT>
-Info reduceInner(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
-    const SparseMatrix<a>* A, Descriptor* desc) {
-  if (desc->struconly()) {
-    // The reference leaves w untouched here (:123-124).
-  } else {
-    if (A->nrows_ == 0) return GrB_INVALID_OBJECT;
-    CHECK(w->allocateGpu());
-    reduceRowsKernel<<<gridFor(static_cast<size_t>(A->nrows_)*32, 256), 256, 0,
-        gbStream()>>>(w->d_val_, A->d_csrRowPtr_, A->d_csrVal_, A->nrows_, op, static_cast<W>(op.identity()));
-    GB_KERNEL_CHECK();
-    w->touched();
-    w->nnz_ = A->nrows_;
-  }
-  return GrB_SUCCESS;
-}
-
-// Dense matrix -> scalar: placeholder, as in the reference (:147-156)
-template <typename T, typename a,
-          typename BinaryOpT,     typename MonoidT>
-Info reduceInner(T* val, BinaryOpT accum, MonoidT op, const DenseMatrix<a>* A,
-    Descriptor* desc) {
-  std::cout << "Error: Dense reduce matrix-to-scalar not implemented yet!\n";
+// ---- sparse matrix rows -> dense vector (out-degrees of PageRank) -------------------
+// Struct-only mode leaves w untouched, as the reference does (:123-124).
+template <typename W, typename a, typename MonoidT>
+Info reduceRows(DenseVector<W>* w, MonoidT op, const SparseMatrix<a>* A, Descriptor* desc) {
+  if (desc->struconly()) return GrB_SUCCESS;
+  if (A->nrows_ == 0) return GrB_INVALID_OBJECT;
+  CHECK(w->allocateGpu());
+  const size_t lanes = static_cast<size_t>(A->nrows_)*32;          // a warp per row
+  reduceRowsKernel<<<gridFor(lanes, 256), 256, 0, gbStream()>>>(w->d_val_,
+      A->d_csrRowPtr_, A->d_csrVal_, A->nrows_, op, static_cast<W>(op.identity()));
+  GB_KERNEL_CHECK();
+  w->touched();
+  w->nnz_ = A->nrows_;
   return GrB_SUCCESS;
 }
 

@@ -1,7 +1,7 @@
 // graphblast_b200 frontend mirror — the one header applications include.
 // Pulls in, in dependency order: the backend selector and the vocabulary (enums,
 // operator/monoid/semiring definitions), the host utilities (Matrix Market reader,
-// CLI flags, COO/CSR helpers, dimension checks), the objects (Descriptor, Vector,
+// CLI flags, COO/CSR helpers), the objects (Descriptor, Vector,
 // Matrix), the operations, and finally the implementation of the selected backend.
 // Same contents as reference graphblas/graphblas.hpp:4-17.
 #ifndef GRAPHBLAS_GRAPHBLAS_HPP_
@@ -15,7 +15,6 @@
 
 // host utilities
 #include <graphblas/util.hpp>
-#include <graphblas/dimension.hpp>
 
 // objects and operations
 #include <graphblas/descriptor.hpp>
