@@ -45,8 +45,9 @@ inline Info& lastStatus() {
   do {                                                                \
     graphblas::Info gb_step__ = (x);                                  \
     if (gb_step__ != graphblas::GrB_SUCCESS) {                        \
-      fprintf(stderr, "Runtime error: %s returned %d at %s:%d\n",     \
-              #x, gb_step__, __FILE__, __LINE__);                     \
+      fprintf(stderr, "Runtime error: %s returned %s (%d) at %s:%d\n",     \
+              #x, graphblas::infoName(gb_step__),                     \
+              static_cast<int>(gb_step__), __FILE__, __LINE__);       \
       graphblas::algorithm::lastStatus() = gb_step__;                 \
       return -1.f;                                                    \
     }                                                                 \

@@ -1,7 +1,8 @@
 // graphblast_b200 frontend mirror — graphblas::Matrix<T>.
-// Method set and argument checks of reference graphblas/matrix.hpp:14-252; calls
-// forward to backend::Matrix<T> held by value as `matrix_` (the CPU verifiers
-// read matrix_.sparse_.h_csr*, reference algorithm/bfs.hpp:101-107).
+// The method set and argument checks of reference graphblas/matrix.hpp:14-252 over a
+// backend::Matrix<T> held by value as `matrix_` (the CPU verifiers read
+// matrix_.sparse_.h_csr*, reference algorithm/bfs.hpp:101-107).  As in vector.hpp a
+// method names its pointer arguments and its backend call; `given` does the rest.
 #ifndef GRAPHBLAS_MATRIX_HPP_
 #define GRAPHBLAS_MATRIX_HPP_
 
@@ -12,104 +13,88 @@
 namespace graphblas {
 template <typename T>
 class Matrix {
- public:
-  Matrix() : matrix_() {}
-  Matrix(Index nrows, Index ncols) : matrix_(nrows, ncols) {}
-  ~Matrix() {}
+  typedef backend::Matrix<T> Impl;
 
-  // C API Methods
+ public:
+  Matrix() {}
+  Matrix(Index nrows, Index ncols) : matrix_(nrows, ncols) {}
+
+  // ---- shape, contents --------------------------------------------------------------------
   Info nnew(Index nrows, Index ncols) {
-    if (nrows == 0 || ncols == 0) return GrB_INVALID_VALUE;
-    return matrix_.nnew(nrows, ncols);
-  }
-  Info dup(const Matrix* rhs) {
-    if (rhs == NULL) return GrB_NULL_POINTER;
-    return matrix_.dup(&rhs->matrix_);
+    return (nrows == 0 || ncols == 0) ? GrB_INVALID_VALUE : matrix_.nnew(nrows, ncols);
   }
   Info clear() { return matrix_.clear(); }
-  Info nrows(Index* nrows) const {
-    if (nrows == NULL) return GrB_NULL_POINTER;
-    return mutableBackend()->nrows(nrows);
+  Info dup(const Matrix* rhs) {
+    return given([&](Impl& m) { return m.dup(&rhs->matrix_); }, rhs);
   }
-  Info ncols(Index* ncols) const {
-    if (ncols == NULL) return GrB_NULL_POINTER;
-    return mutableBackend()->ncols(ncols);
-  }
-  Info nvals(Index* nvals) const {
-    if (nvals == NULL) return GrB_NULL_POINTER;
-    return mutableBackend()->nvals(nvals);
-  }
-  // Host COO triples; empty triples + dat_name means "load the binary cache".
+  void operator=(const Matrix& rhs) { matrix_.dup(&rhs.matrix_); }
+  Info nrows(Index* out) const { return given([&](Impl& m) { return m.nrows(out); }, out); }
+  Info ncols(Index* out) const { return given([&](Impl& m) { return m.ncols(out); }, out); }
+  Info nvals(Index* out) const { return given([&](Impl& m) { return m.nvals(out); }, out); }
+
+  // ---- build ---------------------------------------------------------------------------------
+  // Host COO triples.  The drivers' loader leaves the triples empty when a binary cache
+  // exists: then dat_name alone says what to load (reference matrix.hpp:75-95).
   template <typename BinaryOpT>
-  Info build(const std::vector<Index>* row_indices,
-      const std::vector<Index>* col_indices, const std::vector<T>* values, Index nvals,
-      BinaryOpT dup, char* dat_name = NULL) {
-    if (row_indices == NULL || col_indices == NULL || values == NULL)
-      return GrB_NULL_POINTER;
-    const bool empty = row_indices->empty() && col_indices->empty() &&
-                       values->empty();
-    if (empty && dat_name == NULL) return GrB_NO_VALUE;
-    if (dat_name == NULL || !row_indices->empty())
-      return matrix_.build(row_indices, col_indices, values, nvals, dup,
-          dat_name);
-    return matrix_.build(dat_name);
+  Info build(const std::vector<Index>* row_indices, const std::vector<Index>* col_indices,
+             const std::vector<T>* values, Index nvals, BinaryOpT dup,
+             char* dat_name = NULL) {
+    return given([&](Impl& m) {
+      const bool no_triples = row_indices->empty() && col_indices->empty() && values->empty();
+      if (no_triples && dat_name == NULL) return GrB_NO_VALUE;
+      if (dat_name != NULL && row_indices->empty()) return m.build(dat_name);
+      return m.build(row_indices, col_indices, values, nvals, dup, dat_name);
+    }, row_indices, col_indices, values);
   }
-  Info build(const std::vector<T>* values, Index nvals) {
-    return matrix_.build(values, nvals);
-  }
+  Info build(const std::vector<T>* values, Index nvals) { return matrix_.build(values, nvals); }
   // DEVICE CSR arrays: row_ptr (nrows+1), col_ind (nvals), values (nvals).
-  Info build(Index* row_ptr, Index* col_ind, T* values, Index nvals) {
-    if (row_ptr == NULL || col_ind == NULL || values == NULL)
-      return GrB_NULL_POINTER;
-    if (nvals == 0) return GrB_INVALID_VALUE;
-    return matrix_.build(row_ptr, col_ind, values, nvals);
-  }
-  Info setElement(Index row_index, Index col_index) {
-    return matrix_.setElement(row_index, col_index);
-  }
-  Info extractElement(T* val, Index row_index, Index col_index) {
-    if (val == NULL) return GrB_NULL_POINTER;
-    return matrix_.extractElement(val, row_index, col_index);
-  }
-  Info extractTuples(std::vector<Index>* row_indices, std::vector<Index>* col_indices,
-      std::vector<T>* values, Index* n) {
-    if (row_indices == NULL || col_indices == NULL || values == NULL ||
-        n == NULL)
-      return GrB_NULL_POINTER;
-    return matrix_.extractTuples(row_indices, col_indices, values, n);
-  }
-  Info extractTuples(std::vector<T>* values, Index* n) {
-    if (values == NULL || n == NULL) return GrB_NULL_POINTER;
-    return matrix_.extractTuples(values, n);
+  Info build(Index* d_row_ptr, Index* d_col_ind, T* d_values, Index nvals) {
+    return given([&](Impl& m) {
+      return nvals == 0 ? GrB_INVALID_VALUE : m.build(d_row_ptr, d_col_ind, d_values, nvals);
+    }, d_row_ptr, d_col_ind, d_values);
   }
 
-  // Handy methods
-  void operator=(const Matrix& rhs) { matrix_.dup(&rhs.matrix_); }
+  // ---- element and tuple access ------------------------------------------------------------
+  Info setElement(Index row, Index col) { return matrix_.setElement(row, col); }
+  Info extractElement(T* out, Index row, Index col) {
+    return given([&](Impl& m) { return m.extractElement(out, row, col); }, out);
+  }
+  Info extractTuples(std::vector<Index>* row_indices, std::vector<Index>* col_indices,
+                     std::vector<T>* values, Index* n) {
+    return given([&](Impl& m) { return m.extractTuples(row_indices, col_indices, values, n); },
+                 row_indices, col_indices, values, n);
+  }
+  Info extractTuples(std::vector<T>* values, Index* n) {
+    return given([&](Impl& m) { return m.extractTuples(values, n); }, values, n);
+  }
   const T operator[](Index ind) { return matrix_[ind]; }
-  Info print(bool force_update = false) { return matrix_.print(force_update); }
-  Info check() { return matrix_.check(); }
-  Info setNrows(Index nrows) { return matrix_.setNrows(nrows); }
-  Info setNcols(Index ncols) { return matrix_.setNcols(ncols); }
-  Info resize(Index nrows, Index ncols) { return matrix_.resize(nrows, ncols); }
-  Info setStorage(Storage mat_type) { return matrix_.setStorage(mat_type); }
-  Info getStorage(Storage* mat_type) const {
-    if (mat_type == NULL) return GrB_NULL_POINTER;
-    return matrix_.getStorage(mat_type);
+
+  // ---- handy methods -------------------------------------------------------------------------
+  Info print(bool force_update = false)  { return matrix_.print(force_update); }
+  Info check()                           { return matrix_.check(); }
+  Info setNrows(Index nrows)             { return matrix_.setNrows(nrows); }
+  Info setNcols(Index ncols)             { return matrix_.setNcols(ncols); }
+  Info resize(Index nrows, Index ncols)  { return matrix_.resize(nrows, ncols); }
+  Info setStorage(Storage kind)          { return matrix_.setStorage(kind); }
+  Info getStorage(Storage* out) const {
+    return given([&](Impl& m) { return m.getStorage(out); }, out);
   }
   template <typename U>
-  Info fill(Index axis, Index nvals, U start) {
-    return matrix_.fill(axis, nvals, start);
-  }
+  Info fill(Index axis, Index nvals, U start) { return matrix_.fill(axis, nvals, start); }
   template <typename U>
   Info fillAscending(Index axis, Index nvals, U start) {
     return matrix_.fillAscending(axis, nvals, start);
   }
 
-  backend::Matrix<T> matrix_;
+  Impl matrix_;
 
  private:
-  backend::Matrix<T>* mutableBackend() const {
-    return const_cast<backend::Matrix<T>*>(&matrix_);
+  // `work(backend object)` once none of `needed` is NULL (see vector.hpp).
+  template <typename Work, typename... Pointers>
+  Info given(Work&& work, const Pointers*... needed) const {
+    const bool missing = ((needed == NULL) || ...);
+    if (missing) return GrB_NULL_POINTER;
+    return work(const_cast<Impl&>(matrix_));
   }
 };
 }  // namespace graphblas

@@ -54,61 +54,69 @@ GB_DEFINE_BINARY_OP(select_second, GB_NONE, GB_SAME, GB_SAME, rhs)
 #undef GB_BOOL
 #undef GB_NONE
 
-#define REGISTER_MONOID(M_NAME, BINARYOP, IDENTITY)                          \
-template <typename T_out>                                                    \
-struct M_NAME {                                                              \
-  inline T_out identity() const { return static_cast<T_out>(IDENTITY); }     \
-  inline __host__ __device__ T_out operator()(T_out lhs, T_out rhs) const {  \
-    return BINARYOP<T_out>()(lhs, rhs);                                      \
-  }                                                                          \
-};
+// The vocabulary as two lists — (name, binary operator, identity) and (name, additive
+// monoid, multiplicative operator) — from which the structs are generated.  Names and
+// identities are the reference's (:160-213).  "less" is not a monoid (its two-sided
+// identities differ, it is not associative); it is listed anyway for the SSSP
+// improvement test, as there.
+#define GB_MONOID_LIST(X)                                                     \
+  X(PlusMonoid,       plus,         0)                                        \
+  X(MultipliesMonoid, multiplies,   1)                                        \
+  X(MinimumMonoid,    minimum,      std::numeric_limits<T_out>::max())        \
+  X(MaximumMonoid,    maximum,      0)                                        \
+  X(LogicalOrMonoid,  logical_or,   false)                                    \
+  X(LogicalAndMonoid, logical_and,  false)                                    \
+  X(GreaterMonoid,    greater,      std::numeric_limits<T_out>::min())        \
+  X(CustomLessMonoid, less,         std::numeric_limits<T_out>::max())        \
+  X(NotEqualToMonoid, not_equal_to, std::numeric_limits<T_out>::max())
+
+#define GB_SEMIRING_LIST(X)                                                   \
+  X(LogicalOrAndSemiring,         LogicalOrMonoid,  logical_and)              \
+  X(PlusMultipliesSemiring,       PlusMonoid,       multiplies)               \
+  X(MinimumPlusSemiring,          MinimumMonoid,    plus)                     \
+  X(MaximumMultipliesSemiring,    MaximumMonoid,    multiplies)               \
+  X(PlusDividesSemiring,          PlusMonoid,       divides)                  \
+  X(PlusGreaterSemiring,          PlusMonoid,       greater)                  \
+  X(GreaterPlusSemiring,          GreaterMonoid,    plus)                     \
+  X(PlusMinusSemiring,            PlusMonoid,       minus)                    \
+  X(PlusLessSemiring,             PlusMonoid,       less)                     \
+  X(CustomLessPlusSemiring,       CustomLessMonoid, plus)                     \
+  X(MinimumMultipliesSemiring,    MinimumMonoid,    multiplies)               \
+  X(MultipliesMultipliesSemiring, MultipliesMonoid, multiplies)               \
+  X(NotEqualToPlusSemiring,       NotEqualToMonoid, plus)                     \
+  X(MinimumSelectSecondSemiring,  MinimumMonoid,    select_second)            \
+  X(PlusNotEqualToSemiring,       PlusMonoid,       not_equal_to)             \
+  X(CustomLessLessSemiring,       CustomLessMonoid, less)                     \
+  X(MinimumNotEqualToSemiring,    MinimumMonoid,    not_equal_to)
 
 namespace graphblas {
-REGISTER_MONOID(PlusMonoid,       plus,         0)
-REGISTER_MONOID(MultipliesMonoid, multiplies,   1)
-REGISTER_MONOID(MinimumMonoid,    minimum,      std::numeric_limits<T_out>::max())
-REGISTER_MONOID(MaximumMonoid,    maximum,      0)
-REGISTER_MONOID(LogicalOrMonoid,  logical_or,   false)
-REGISTER_MONOID(LogicalAndMonoid, logical_and,  false)
-REGISTER_MONOID(GreaterMonoid,    greater,      std::numeric_limits<T_out>::min())
-// "less" is not a monoid (two-sided identities differ, not associative); the
-// reference registers it anyway for the SSSP improvement test.
-REGISTER_MONOID(CustomLessMonoid, less,         std::numeric_limits<T_out>::max())
-REGISTER_MONOID(NotEqualToMonoid, not_equal_to, std::numeric_limits<T_out>::max())
-}  // namespace graphblas
 
-#define REGISTER_SEMIRING(SR_NAME, ADD_MONOID, MULT_BINARYOP)                \
-template <typename T_in1, typename T_in2 = T_in1, typename T_out = T_in1>    \
-struct SR_NAME {                                                             \
-  typedef T_out result_type;                                                 \
-  typedef T_out T_out_type;                                                  \
-  inline T_out identity() const { return ADD_MONOID<T_out>().identity(); }   \
-  inline __host__ __device__ T_out add_op(T_out lhs, T_out rhs) {            \
-    return ADD_MONOID<T_out>()(lhs, rhs);                                    \
-  }                                                                          \
-  inline __host__ __device__ T_out mul_op(T_in1 lhs, T_in2 rhs) {            \
-    return MULT_BINARYOP<T_in1, T_in2, T_out>()(lhs, rhs);                   \
-  }                                                                          \
+#define GB_MAKE_MONOID(NAME, OP, IDENTITY)                                    \
+template <typename T_out>                                                     \
+struct NAME {                                                                 \
+  inline T_out identity() const { return static_cast<T_out>(IDENTITY); }      \
+  inline __host__ __device__ T_out operator()(T_out lhs, T_out rhs) const {   \
+    return OP<T_out>()(lhs, rhs);                                             \
+  }                                                                           \
 };
+GB_MONOID_LIST(GB_MAKE_MONOID)
+#undef GB_MAKE_MONOID
 
-namespace graphblas {
-REGISTER_SEMIRING(LogicalOrAndSemiring,         LogicalOrMonoid,  logical_and)
-REGISTER_SEMIRING(PlusMultipliesSemiring,       PlusMonoid,       multiplies)
-REGISTER_SEMIRING(MinimumPlusSemiring,          MinimumMonoid,    plus)
-REGISTER_SEMIRING(MaximumMultipliesSemiring,    MaximumMonoid,    multiplies)
-REGISTER_SEMIRING(PlusDividesSemiring,          PlusMonoid,       divides)
-REGISTER_SEMIRING(PlusGreaterSemiring,          PlusMonoid,       greater)
-REGISTER_SEMIRING(GreaterPlusSemiring,          GreaterMonoid,    plus)
-REGISTER_SEMIRING(PlusMinusSemiring,            PlusMonoid,       minus)
-REGISTER_SEMIRING(PlusLessSemiring,             PlusMonoid,       less)
-REGISTER_SEMIRING(CustomLessPlusSemiring,       CustomLessMonoid, plus)
-REGISTER_SEMIRING(MinimumMultipliesSemiring,    MinimumMonoid,    multiplies)
-REGISTER_SEMIRING(MultipliesMultipliesSemiring, MultipliesMonoid, multiplies)
-REGISTER_SEMIRING(NotEqualToPlusSemiring,       NotEqualToMonoid, plus)
-REGISTER_SEMIRING(MinimumSelectSecondSemiring,  MinimumMonoid,    select_second)
-REGISTER_SEMIRING(PlusNotEqualToSemiring,       PlusMonoid,       not_equal_to)
-REGISTER_SEMIRING(CustomLessLessSemiring,       CustomLessMonoid, less)
-REGISTER_SEMIRING(MinimumNotEqualToSemiring,    MinimumMonoid,    not_equal_to)
+#define GB_MAKE_SEMIRING(NAME, ADD, MUL)                                      \
+template <typename T_in1, typename T_in2 = T_in1, typename T_out = T_in1>     \
+struct NAME {                                                                 \
+  typedef T_out result_type;                                                  \
+  typedef T_out T_out_type;                                                   \
+  inline T_out identity() const { return ADD<T_out>().identity(); }           \
+  inline __host__ __device__ T_out add_op(T_out lhs, T_out rhs) {             \
+    return ADD<T_out>()(lhs, rhs);                                            \
+  }                                                                           \
+  inline __host__ __device__ T_out mul_op(T_in1 lhs, T_in2 rhs) {             \
+    return MUL<T_in1, T_in2, T_out>()(lhs, rhs);                              \
+  }                                                                           \
+};
+GB_SEMIRING_LIST(GB_MAKE_SEMIRING)
+#undef GB_MAKE_SEMIRING
 
 // Functor views of a semiring's two operations (what kernels are templated on).
 template <typename SemiringT, bool IsAdd>

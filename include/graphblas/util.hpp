@@ -41,8 +41,9 @@
   do {                                                          \
     graphblas::Info gb_status__ = (x);                          \
     if (gb_status__ != graphblas::GrB_SUCCESS) {                \
-      fprintf(stderr, "Runtime error: %s returned %d at %s:%d\n", \
-              #x, gb_status__, __FILE__, __LINE__);             \
+      fprintf(stderr, "Runtime error: %s returned %s (%d) at %s:%d\n", \
+              #x, graphblas::infoName(gb_status__),             \
+              static_cast<int>(gb_status__), __FILE__, __LINE__); \
       on_error;                                                 \
     }                                                           \
   } while (0)

@@ -1,6 +1,9 @@
 // graphblast_b200 frontend mirror — graphblas::Vector<T>.
-// Method set and NULL-argument behaviour of reference graphblas/vector.hpp:13-264;
-// every call forwards to backend::Vector<T> held by value as `vector_`.
+// The method set of reference graphblas/vector.hpp:13-264 over a backend::Vector<T>
+// held by value as `vector_`.  Every method is the same two steps — a pointer argument
+// that is missing answers GrB_NULL_POINTER, otherwise the backend object does the work
+// — so they are written once (`given`) and each method only names its pointers and its
+// backend call.
 #ifndef GRAPHBLAS_VECTOR_HPP_
 #define GRAPHBLAS_VECTOR_HPP_
 
@@ -11,91 +14,89 @@
 namespace graphblas {
 template <typename T>
 class Vector {
- public:
-  Vector() : vector_() {}
-  explicit Vector(Index nsize) : vector_(nsize) {}
-  ~Vector() {}
+  typedef backend::Vector<T> Impl;
 
-  // C API Methods
-  Info nnew(Index nsize) { return vector_.nnew(nsize); }
+ public:
+  Vector() {}
+  explicit Vector(Index nsize) : vector_(nsize) {}
+
+  // ---- size, contents -------------------------------------------------------------------
+  Info nnew(Index nsize)      { return vector_.nnew(nsize); }
+  Info clear()                { return vector_.clear(); }
   Info dup(const Vector* rhs) { return vector_.dup(&rhs->vector_); }
-  Info clear() { return vector_.clear(); }
-  Info size(Index* nsize) const {
-    if (nsize == NULL) return GrB_NULL_POINTER;
-    return mutableBackend()->size(nsize);
+  void operator=(const Vector& rhs) { vector_.dup(&rhs.vector_); }
+  Info size(Index* out) const  { return given([&](Impl& v) { return v.size(out); }, out); }
+  Info nvals(Index* out) const { return given([&](Impl& v) { return v.nvals(out); }, out); }
+  Info swap(Vector* other) {  // NOLINT(build/include_what_you_use)
+    return given([&](Impl& v) { return v.swap(&other->vector_); }, other);
   }
-  Info nvals(Index* nvals) const {
-    if (nvals == NULL) return GrB_NULL_POINTER;
-    return mutableBackend()->nvals(nvals);
-  }
+
+  // ---- build: host tuples, host values, adopted device arrays ---------------------------
   template <typename BinaryOpT>
-  Info build(const std::vector<Index>* indices, const std::vector<T>* values,
-      Index nvals, BinaryOpT dup) {
-    if (indices == NULL || values == NULL) return GrB_NULL_POINTER;
-    return vector_.build(indices, values, nvals, dup);
+  Info build(const std::vector<Index>* indices, const std::vector<T>* values, Index nvals,
+             BinaryOpT dup) {
+    return given([&](Impl& v) { return v.build(indices, values, nvals, dup); }, indices,
+                 values);
   }
   Info build(const std::vector<T>* values, Index nvals) {
-    if (values == NULL) return GrB_NULL_POINTER;
-    return vector_.build(values, nvals);
+    return given([&](Impl& v) { return v.build(values, nvals); }, values);
   }
-  // Device pointers, adopted
-  Info build(Index* indices, T* values, Index nvals) {
-    if (indices == NULL || values == NULL) return GrB_NULL_POINTER;
-    if (nvals == 0) return GrB_INVALID_VALUE;
-    return vector_.build(indices, values, nvals);
+  Info build(Index* d_indices, T* d_values, Index nvals) {
+    return given([&](Impl& v) {
+      return nvals == 0 ? GrB_INVALID_VALUE : v.build(d_indices, d_values, nvals);
+    }, d_indices, d_values);
   }
-  Info build(T* values, Index nvals) {
-    if (values == NULL) return GrB_NULL_POINTER;
-    if (nvals == 0) return GrB_INVALID_VALUE;
-    return vector_.build(values, nvals);
-  }
-  Info setElement(T val, Index index) { return vector_.setElement(val, index); }
-  Info extractElement(T* val, Index index) {
-    if (val == NULL) return GrB_NULL_POINTER;
-    return vector_.extractElement(val, index);
-  }
-  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n) {
-    if (indices == NULL || values == NULL || n == NULL) return GrB_NULL_POINTER;
-    return vector_.extractTuples(indices, values, n);
-  }
-  Info extractTuples(std::vector<T>* values, Index* n) {
-    if (values == NULL || n == NULL) return GrB_NULL_POINTER;
-    return vector_.extractTuples(values, n);
+  Info build(T* d_values, Index nvals) {
+    return given([&](Impl& v) {
+      return nvals == 0 ? GrB_INVALID_VALUE : v.build(d_values, nvals);
+    }, d_values);
   }
 
-  // Handy methods
-  void operator=(const Vector& rhs) { vector_.dup(&rhs.vector_); }
-  const T& operator[](Index ind) { return vector_[ind]; }
-  Info resize(Index nvals) { return vector_.resize(nvals); }
-  Info fill(T val) { return vector_.fill(val); }
-  Info fillAscending(Index nvals) { return vector_.fillAscending(nvals); }
-  Info print(bool force_update = false) { return vector_.print(force_update); }
-  Info countUnique(Index* count) {
-    if (count == NULL) return GrB_NULL_POINTER;
-    return vector_.countUnique(count);
+  // ---- element and tuple access ----------------------------------------------------------
+  Info setElement(T val, Index index) { return vector_.setElement(val, index); }
+  Info extractElement(T* out, Index index) {
+    return given([&](Impl& v) { return v.extractElement(out, index); }, out);
   }
-  Info setStorage(Storage vec_type) { return vector_.setStorage(vec_type); }
-  Info getStorage(Storage* vec_type) const {
-    if (vec_type == NULL) return GrB_NULL_POINTER;
-    return vector_.getStorage(vec_type);
+  Info extractTuples(std::vector<Index>* indices, std::vector<T>* values, Index* n) {
+    return given([&](Impl& v) { return v.extractTuples(indices, values, n); }, indices,
+                 values, n);
+  }
+  Info extractTuples(std::vector<T>* values, Index* n) {
+    return given([&](Impl& v) { return v.extractTuples(values, n); }, values, n);
+  }
+  const T& operator[](Index ind) { return vector_[ind]; }
+
+  // ---- handy methods ------------------------------------------------------------------------
+  Info resize(Index nvals)               { return vector_.resize(nvals); }
+  Info fill(T val)                       { return vector_.fill(val); }
+  Info fillAscending(Index nvals)        { return vector_.fillAscending(nvals); }
+  Info print(bool force_update = false)  { return vector_.print(force_update); }
+  Info countUnique(Index* out) {
+    return given([&](Impl& v) { return v.countUnique(out); }, out);
+  }
+
+  // ---- storage (sparse <-> dense) ---------------------------------------------------------
+  Info setStorage(Storage kind) { return vector_.setStorage(kind); }
+  Info getStorage(Storage* out) const {
+    return given([&](Impl& v) { return v.getStorage(out); }, out);
   }
   Info sparse2dense(T identity, Descriptor* desc = NULL) {
-    return vector_.sparse2dense(identity,
-        desc == NULL ? NULL : &desc->descriptor_);
+    return vector_.sparse2dense(identity, desc ? &desc->descriptor_ : NULL);
   }
   Info dense2sparse(T identity, Descriptor* desc) {
     return vector_.dense2sparse(identity, &desc->descriptor_);
   }
-  Info swap(Vector* rhs) {  // NOLINT(build/include_what_you_use)
-    if (rhs == NULL) return GrB_NULL_POINTER;
-    return vector_.swap(&rhs->vector_);
-  }
 
-  backend::Vector<T> vector_;
+  Impl vector_;
 
  private:
-  backend::Vector<T>* mutableBackend() const {
-    return const_cast<backend::Vector<T>*>(&vector_);
+  // `work(backend object)` once none of `needed` is NULL.  const methods of the
+  // reference call non-const backend methods: the backend object is handed out mutable.
+  template <typename Work, typename... Pointers>
+  Info given(Work&& work, const Pointers*... needed) const {
+    const bool missing = ((needed == NULL) || ...);
+    if (missing) return GrB_NULL_POINTER;
+    return work(const_cast<Impl&>(vector_));
   }
 };
 }  // namespace graphblas
