@@ -42,7 +42,9 @@ namespace backend {
 
 #define GB_HASH_EMPTY   (-1)
 #define GB_HASH_CAP_S   64       // warp-owned tables: 256 slots, load <= 0.25
+#ifndef GB_HASH_CAP_M
 #define GB_HASH_CAP_M   1024     // CTA-owned tables
+#endif
 #define GB_HASH_SLOTS_S 256
 #ifndef GB_HASH_SLOTS_M
 #define GB_HASH_SLOTS_M 2048     // load <= 0.5: a probe reads four slots, chains stay short
