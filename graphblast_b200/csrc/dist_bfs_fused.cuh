@@ -34,7 +34,9 @@
 
 // CTA shape of the distributed traversal kernel (validated at 2 and 8 GPUs with this
 // shape; the single-GPU kernel chooses its own, kernels/bfs_fused.cuh)
+#ifndef GBX_BFS_NT
 #define GBX_BFS_NT 1024
+#endif
 
 namespace gbx {
 
