@@ -79,6 +79,19 @@ def test_descriptor_host_logic_without_device():
         d.set_knob("mxvmode", 7)
     with pytest.raises(gb.GraphBLASError):
         d.set_knob("no_such_knob", 1)
+    # every numeric command-line knob goes through the same enumeration
+    # (backend descriptor.hpp: eachKnob), whatever its type
+    for name, value in [("niter", 3), ("timing", 2), ("directed", 1), ("ta", 8),
+                        ("memusage", 0.5), ("switchpoint", 0.25), ("opreuse", 1),
+                        ("dirinfo", 1), ("atomic", 1), ("debug", 0), ("ndevice", 1)]:
+        d.set_knob(name, value)
+        assert d.get_knob(name) == pytest.approx(value), name
+    assert d.get_knob("opreuse") == 1 and d.get_knob("struconly") == 0
+    d.set_knob("nthread", 256)                       # GrB_NT follows a valid thread count
+    assert int(d.get(gb.Desc_field.GrB_NT)) == 256         # Desc_value GrB_256
+    assert d.get_knob("mxvmode") == 0                # the rejected value left no trace
+    with pytest.raises(gb.GraphBLASError):
+        d.set_knob("mode", 1)                        # a string knob is not settable by number
 
 
 def test_no_cpu_fallback_without_device():
