@@ -8,8 +8,9 @@
 // be produced one after the other in storage order.  That is why apply runs on the
 // host when the descriptor's GrB_BACKEND is GrB_SEQUENTIAL — the only mode any
 // caller uses — and mirrors the result to the device; outside every timed region.
-// One routine serves all containers: they only differ in where their value array
-// lives and how they are mirrored back.
+// One routine serves all containers (dense vector, sparse vector, sparse matrix; dense
+// matrices are outside the hot path and answered by operations.hpp): they only differ
+// in where their value array lives and how they are mirrored back.
 #ifndef GRAPHBLAS_BACKEND_CUDA_APPLY_HPP_
 #define GRAPHBLAS_BACKEND_CUDA_APPLY_HPP_
 
@@ -57,34 +58,6 @@ Info applyStored(Out* out, const MaskT* mask, UnaryOpT op, In* in, Descriptor* d
   for (Index k = 0; k < n; ++k)
     apply_detail::values(out)[k] = op(apply_detail::values(in)[k]);
   return apply_detail::publish(out);
-}
-
-template <typename U, typename W, typename M,
-          typename BinaryOpT, typename UnaryOpT>
-Info applyDense(DenseVector<W>* w, const Vector<M>* mask, BinaryOpT accum, UnaryOpT op,
-    DenseVector<U>* u, Descriptor* desc) {
-  return applyStored(w, mask, op, u, desc, "a dense vector");
-}
-
-template <typename U, typename W, typename M,
-          typename BinaryOpT, typename UnaryOpT>
-Info applySparse(SparseVector<W>* w, const Vector<M>* mask, BinaryOpT accum,
-    UnaryOpT op, SparseVector<U>* u, Descriptor* desc) {
-  return applyStored(w, mask, op, u, desc, "a sparse vector");
-}
-
-template <typename a, typename c, typename m,
-          typename BinaryOpT, typename UnaryOpT>
-Info applyDense(DenseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, UnaryOpT op,
-    DenseMatrix<a>* A, Descriptor* desc) {
-  return GrB_NOT_IMPLEMENTED;          // dense matrices are outside the hot path
-}
-
-template <typename a, typename c, typename m,
-          typename BinaryOpT, typename UnaryOpT>
-Info applySparse(SparseMatrix<c>* C, const Matrix<m>* mask, BinaryOpT accum,
-    UnaryOpT op, SparseMatrix<a>* A, Descriptor* desc) {
-  return applyStored(C, mask, op, A, desc, "a sparse matrix");
 }
 
 }  // namespace backend

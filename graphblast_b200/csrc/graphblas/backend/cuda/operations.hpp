@@ -65,8 +65,8 @@ inline OperandPair pairOf(Storage first, Storage second) {
   return GB_PAIR_INVALID;
 }
 
-template <typename U, typename V>
-OperandPair pairOf(const Vector<U>* u, const Vector<V>* v) {
+template <typename TU, typename TV>
+OperandPair pairOf(const Vector<TU>* u, const Vector<TV>* v) {
   return pairOf(u->vec_type_, v->vec_type_);
 }
 
@@ -94,10 +94,10 @@ GB_DECLARED_ONLY(graphColor,        "graphColor (cuSPARSE csrcolor, gone from CU
 GB_DECLARED_ONLY(applyVxm,          "applyVxm")
 #undef GB_DECLARED_ONLY
 
-template <typename c, typename a, typename b, typename m,
-          typename BinaryOpT,     typename SemiringT>
-Info mxm(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
-    const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
+template <typename TC, typename TA, typename TB, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info mxm(Matrix<TC>* C, const Matrix<TMask>* mask, AccumT accum, SemiringT op,
+    const Matrix<TA>* A, const Matrix<TB>* B, Descriptor* desc) {
   if (!A->isSparse() || !B->isSparse()) return notBuilt("mxm with a dense operand (SpMM / GEMM)");
   if (mask == NULL) return notBuilt("unmasked SpGEMM");
   CHECK(C->setStorage(GrB_SPARSE));
@@ -107,11 +107,11 @@ Info mxm(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
 // Shared body of vxm / mxv once the descriptor says which side is transposed.
 // Step 1 puts the input vector into the storage the direction needs, step 2 runs
 // the push (sparse input) or the pull (dense input).
-template <bool IsVxm, typename W, typename U, typename a, typename M,
-          typename BinaryOpT, typename SemiringT>
-Info mxvDispatch(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
-    const Matrix<a>* A, const Vector<U>* u, Descriptor* desc) {
-  Vector<U>* input = const_cast<Vector<U>*>(u);
+template <bool IsVxm, typename TW, typename TU, typename TA, typename TMask,
+          typename AccumT, typename SemiringT>
+Info mxvDispatch(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, SemiringT op,
+    const Matrix<TA>* A, const Vector<TU>* u, Descriptor* desc) {
+  Vector<TU>* input = const_cast<Vector<TU>*>(u);
   if (!A->isSparse()) return notBuilt("mxv / vxm with a dense matrix (GEMV)");
 
   SparseMatrixFormat format;
@@ -124,7 +124,7 @@ Info mxvDispatch(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT
   const bool both_orientations = reported_symmetric || format == GrB_SPARSE_MATRIX_CSRCSC;
 
   // ---- step 1: storage of the input ------------------------------------------------
-  const U identity = op.identity();
+  const TU identity = op.identity();
   const bool dense_in = (input->vec_type_ == GrB_DENSE);
   const bool sparse_in = (input->vec_type_ == GrB_SPARSE);
   if (one_orientation) {
@@ -184,10 +184,10 @@ void traceVector(Descriptor* desc, const char* banner, const Vector<X>* x) {
 }
 
 // vxm = mxv on the transposed matrix: GrB_INP1 is toggled around the call.
-template <typename W, typename U, typename a, typename M,
-          typename BinaryOpT, typename SemiringT>
-Info vxm(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
-    const Vector<U>* u, const Matrix<a>* A, Descriptor* desc) {
+template <typename TW, typename TU, typename TA, typename TMask,
+          typename AccumT, typename SemiringT>
+Info vxm(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, SemiringT op,
+    const Vector<TU>* u, const Matrix<TA>* A, Descriptor* desc) {
   traceVector(desc, "===Begin vxm===", u);
   Desc_value inp0_mode;
   CHECK(desc->get(GrB_INP0, &inp0_mode));
@@ -199,10 +199,10 @@ Info vxm(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
   return status;
 }
 
-template <typename W, typename a, typename U, typename M,
-          typename BinaryOpT, typename SemiringT>
-Info mxv(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
-    const Matrix<a>* A, const Vector<U>* u, Descriptor* desc) {
+template <typename TW, typename TA, typename TU, typename TMask,
+          typename AccumT, typename SemiringT>
+Info mxv(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, SemiringT op,
+    const Matrix<TA>* A, const Vector<TU>* u, Descriptor* desc) {
   traceVector(desc, "===Begin mxv===", u);
   Desc_value inp1_mode;
   CHECK(desc->get(GrB_INP1, &inp1_mode));
@@ -215,13 +215,13 @@ Info mxv(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
 // w = u .* v.  Results: dense x dense -> dense (sparse when the mask is sparse),
 // anything with a sparse operand -> sparse; sparse x sparse reads v as dense, as
 // the reference does by flipping its tag (operations.hpp:365-371).
-template <typename W, typename U, typename V, typename M,
-          typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
-    const Vector<U>* u, const Vector<V>* v, Descriptor* desc) {
+template <typename TW, typename TU, typename TV, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info eWiseMult(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, SemiringT op,
+    const Vector<TU>* u, const Vector<TV>* v, Descriptor* desc) {
   CHECK(settle(u, v, w, mask));
   if (pairOf(u, v) == GB_PAIR_SPARSE_SPARSE)
-    CHECK(const_cast<Vector<V>*>(v)->setStorage(GrB_DENSE));
+    CHECK(const_cast<Vector<TV>*>(v)->setStorage(GrB_DENSE));
   switch (pairOf(u, v)) {
     case GB_PAIR_DENSE_DENSE:
       if (mask != NULL && mask->vec_type_ == GrB_SPARSE) {
@@ -245,18 +245,18 @@ Info eWiseMult(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT o
   }
 }
 
-template <typename c, typename a, typename b, typename m,
-          typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
-    const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
+template <typename TC, typename TA, typename TB, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info eWiseMult(Matrix<TC>* C, const Matrix<TMask>* mask, AccumT accum, SemiringT op,
+    const Matrix<TA>* A, const Matrix<TB>* B, Descriptor* desc) {
   return notBuilt("eWiseMult of two matrices");
 }
 
 // Extension: matrix (x) broadcast scalar
-template <typename c, typename a, typename b, typename m,
-          typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
-    const Matrix<a>* A, b val, Descriptor* desc) {
+template <typename TC, typename TA, typename TB, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info eWiseMult(Matrix<TC>* C, const Matrix<TMask>* mask, AccumT accum, SemiringT op,
+    const Matrix<TA>* A, TB val, Descriptor* desc) {
   if (A->isDense()) return notBuilt("eWiseMult of a dense matrix and a scalar");
   if (!A->isSparse()) return GrB_INVALID_OBJECT;
   if (mask != NULL) return notBuilt("masked eWiseMult of a matrix and a scalar");
@@ -266,10 +266,10 @@ Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT o
 
 // Extension: matrix (x) broadcast vector (column vector; row vector when
 // GrB_INP1 is GrB_TRAN)
-template <typename c, typename a, typename b, typename m,
-          typename BinaryOpT,     typename SemiringT>
-Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
-    const Matrix<a>* A, const Vector<b>* B, Descriptor* desc) {
+template <typename TC, typename TA, typename TB, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info eWiseMult(Matrix<TC>* C, const Matrix<TMask>* mask, AccumT accum, SemiringT op,
+    const Matrix<TA>* A, const Vector<TB>* B, Descriptor* desc) {
   Desc_value inp0_mode, inp1_mode;
   CHECK(desc->get(GrB_INP0, &inp0_mode));
   CHECK(desc->get(GrB_INP1, &inp1_mode));
@@ -288,16 +288,16 @@ Info eWiseMult(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT o
 
 // w = u + v, always dense.  A sparse operand that is also the output is
 // densified first (reference :598-607).
-template <typename W, typename U, typename V, typename M,
-          typename BinaryOpT,     typename SemiringT>
-Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
-    const Vector<U>* u, const Vector<V>* v, Descriptor* desc) {
+template <typename TW, typename TU, typename TV, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info eWiseAdd(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, SemiringT op,
+    const Vector<TU>* u, const Vector<TV>* v, Descriptor* desc) {
   CHECK(settle(u, v, w, mask));
   const void* out = reinterpret_cast<const void*>(w);
   if (reinterpret_cast<const void*>(u) == out && u->vec_type_ == GrB_SPARSE)
-    const_cast<Vector<U>*>(u)->sparse2dense(op.identity(), desc);
+    const_cast<Vector<TU>*>(u)->sparse2dense(op.identity(), desc);
   else if (reinterpret_cast<const void*>(v) == out && v->vec_type_ == GrB_SPARSE)
-    const_cast<Vector<V>*>(v)->sparse2dense(op.identity(), desc);
+    const_cast<Vector<TV>*>(v)->sparse2dense(op.identity(), desc);
   const OperandPair pair = pairOf(u, v);
   CHECK(w->setStorage(GrB_DENSE));
   switch (pair) {
@@ -317,18 +317,18 @@ Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op
   }
 }
 
-template <typename c, typename a, typename b, typename m,
-          typename BinaryOpT,     typename SemiringT>
-Info eWiseAdd(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, SemiringT op,
-    const Matrix<a>* A, const Matrix<b>* B, Descriptor* desc) {
+template <typename TC, typename TA, typename TB, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info eWiseAdd(Matrix<TC>* C, const Matrix<TMask>* mask, AccumT accum, SemiringT op,
+    const Matrix<TA>* A, const Matrix<TB>* B, Descriptor* desc) {
   return notBuilt("eWiseAdd of two matrices");
 }
 
 // Extension: vector (+) broadcast scalar
-template <typename W, typename U, typename V, typename M,
-          typename BinaryOpT,     typename SemiringT>
-Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op,
-    const Vector<U>* u, V val, Descriptor* desc) {
+template <typename TW, typename TU, typename TV, typename TMask,
+          typename AccumT,     typename SemiringT>
+Info eWiseAdd(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, SemiringT op,
+    const Vector<TU>* u, TV val, Descriptor* desc) {
   CHECK(settle(u, w));
   const Storage u_type = u->vec_type_;
   if (u_type != GrB_DENSE && u_type != GrB_SPARSE) return GrB_INVALID_OBJECT;
@@ -342,9 +342,9 @@ Info eWiseAdd(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, SemiringT op
 // Masked constant assign.  The target is written in part, so its lazily held
 // values are written out first; a dense mask is read through its bitmap shadow
 // when that is current, except by the sparse-target filter, which reads values.
-template <typename W, typename T, typename M,
-          typename BinaryOpT>
-Info assign(Vector<W>* w, Vector<M>* mask, BinaryOpT accum, T val,
+template <typename TW, typename TS, typename TMask,
+          typename AccumT>
+Info assign(Vector<TW>* w, Vector<TMask>* mask, AccumT accum, TS val,
     const Vector<Index>* indices, Index nindices, Descriptor* desc) {
   if (desc->debug()) std::cout << "===Begin assign===\nInput: " << val << std::endl;
   CHECK(settle(w));
@@ -361,44 +361,41 @@ Info assign(Vector<W>* w, Vector<M>* mask, BinaryOpT accum, T val,
   return GrB_SUCCESS;
 }
 
-template <typename W, typename U, typename M,
-          typename BinaryOpT,     typename UnaryOpT>
-Info apply(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, UnaryOpT op,
-    const Vector<U>* u, Descriptor* desc) {
-  Vector<U>* source = const_cast<Vector<U>*>(u);
+template <typename TW, typename TU, typename TMask,
+          typename AccumT,     typename UnaryOpT>
+Info apply(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, UnaryOpT op,
+    const Vector<TU>* u, Descriptor* desc) {
+  Vector<TU>* source = const_cast<Vector<TU>*>(u);
   CHECK(settle(u, w, mask));
   if (u->vec_type_ == GrB_SPARSE) {
     CHECK(w->setStorage(GrB_SPARSE));
-    return applySparse(&w->sparse_, mask, accum, op, &source->sparse_, desc);
+    return applyStored(&w->sparse_, mask, op, &source->sparse_, desc, "a sparse vector");
   }
   if (u->vec_type_ == GrB_DENSE) {
     CHECK(w->setStorage(GrB_DENSE));
-    return applyDense(&w->dense_, mask, accum, op, &source->dense_, desc);
+    return applyStored(&w->dense_, mask, op, &source->dense_, desc, "a dense vector");
   }
   return GrB_UNINITIALIZED_OBJECT;
 }
 
-template <typename c, typename a, typename m,
-          typename BinaryOpT,     typename UnaryOpT>
-Info apply(Matrix<c>* C, const Matrix<m>* mask, BinaryOpT accum, UnaryOpT op,
-    const Matrix<a>* A, Descriptor* desc) {
-  Matrix<a>* source = const_cast<Matrix<a>*>(A);
+template <typename TC, typename TA, typename TMask,
+          typename AccumT,     typename UnaryOpT>
+Info apply(Matrix<TC>* C, const Matrix<TMask>* mask, AccumT accum, UnaryOpT op,
+    const Matrix<TA>* A, Descriptor* desc) {
+  Matrix<TA>* source = const_cast<Matrix<TA>*>(A);
   if (A->isSparse()) {
     CHECK(C->setStorage(GrB_SPARSE));
-    return applySparse(&C->sparse_, mask, accum, op, &source->sparse_, desc);
+    return applyStored(&C->sparse_, mask, op, &source->sparse_, desc, "a sparse matrix");
   }
-  if (A->isDense()) {
-    CHECK(C->setStorage(GrB_DENSE));
-    return applyDense(&C->dense_, mask, accum, op, &source->dense_, desc);
-  }
+  if (A->isDense()) return notBuilt("apply on a dense matrix");
   return GrB_UNINITIALIZED_OBJECT;
 }
 
 // matrix rows -> vector
-template <typename W, typename a, typename M,
-          typename BinaryOpT,     typename MonoidT>
-Info reduce(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
-    const Matrix<a>* A, Descriptor* desc) {
+template <typename TW, typename TA, typename TMask,
+          typename AccumT,     typename MonoidT>
+Info reduce(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum, MonoidT op,
+    const Matrix<TA>* A, Descriptor* desc) {
   CHECK(w->setStorage(GrB_DENSE));
   if (mask != NULL) return notBuilt("masked reduce");
   if (A->isSparse()) return reduceRows(&w->dense_, op, &A->sparse_, desc);
@@ -407,13 +404,13 @@ Info reduce(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum, MonoidT op,
 }
 
 // vector -> scalar
-template <typename T, typename U,
-          typename BinaryOpT, typename MonoidT>
-Info reduce(T* val, BinaryOpT accum, MonoidT op, const Vector<U>* u, Descriptor* desc) {
+template <typename TS, typename TU,
+          typename AccumT, typename MonoidT>
+Info reduce(TS* val, AccumT accum, MonoidT op, const Vector<TU>* u, Descriptor* desc) {
   if (u->vec_type_ == GrB_SPARSE)
     CHECK(reduceStored(val, accum, op, &u->sparse_, desc));
   else if (u->vec_type_ == GrB_DENSE)
-    CHECK(reduceDense(val, accum, op, const_cast<DenseVector<U>*>(&u->dense_), desc));
+    CHECK(reduceDense(val, accum, op, const_cast<DenseVector<TU>*>(&u->dense_), desc));
   else
     return GrB_UNINITIALIZED_OBJECT;
   if (desc->debug()) std::cout << "reduce output: " << *val << std::endl;
@@ -421,9 +418,9 @@ Info reduce(T* val, BinaryOpT accum, MonoidT op, const Vector<U>* u, Descriptor*
 }
 
 // matrix -> scalar
-template <typename T, typename a,
-          typename BinaryOpT,     typename MonoidT>
-Info reduce(T* val, BinaryOpT accum, MonoidT op, const Matrix<a>* A, Descriptor* desc) {
+template <typename TS, typename TA,
+          typename AccumT,     typename MonoidT>
+Info reduce(TS* val, AccumT accum, MonoidT op, const Matrix<TA>* A, Descriptor* desc) {
   if (A->isSparse()) return reduceStored(val, accum, op, &A->sparse_, desc);
   if (A->isDense())  return notBuilt("reduce of a dense matrix to a scalar");
   return GrB_UNINITIALIZED_OBJECT;
@@ -431,28 +428,28 @@ Info reduce(T* val, BinaryOpT accum, MonoidT op, const Matrix<a>* A, Descriptor*
 
 // ---- index-driven vector operations (indexed.hpp) ------------------------------
 
-template <typename W, typename M, typename U, typename T>
-Info scatter(Vector<W>* w, const Vector<M>* mask, const Vector<U>* u, T val,
+template <typename TW, typename TMask, typename TU, typename TS>
+Info scatter(Vector<TW>* w, const Vector<TMask>* mask, const Vector<TU>* u, TS val,
     Descriptor* desc) {
   return scatterConstant(w, mask, u, val, desc);
 }
 
-template <typename W, typename U, typename M, typename I,
-          typename BinaryOpT>
-Info assignScatter(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
-    const Vector<U>* u, const Vector<I>* indices, Descriptor* desc) {
+template <typename TW, typename TU, typename TMask, typename TIndex,
+          typename AccumT>
+Info assignScatter(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum,
+    const Vector<TU>* u, const Vector<TIndex>* indices, Descriptor* desc) {
   return indexedMove<false>(w, mask, u, indices, desc);
 }
 
-template <typename W, typename U, typename M, typename I,
-          typename BinaryOpT>
-Info extractGather(Vector<W>* w, const Vector<M>* mask, BinaryOpT accum,
-    const Vector<U>* u, const Vector<I>* indices, Descriptor* desc) {
+template <typename TW, typename TU, typename TMask, typename TIndex,
+          typename AccumT>
+Info extractGather(Vector<TW>* w, const Vector<TMask>* mask, AccumT accum,
+    const Vector<TU>* u, const Vector<TIndex>* indices, Descriptor* desc) {
   return indexedMove<true>(w, mask, u, indices, desc);
 }
 
-template <typename c, typename a>
-Info tril(Matrix<c>* C, Matrix<a>* A, Descriptor* desc) {
+template <typename TC, typename TA>
+Info tril(Matrix<TC>* C, Matrix<TA>* A, Descriptor* desc) {
   if (reinterpret_cast<void*>(C) != reinterpret_cast<void*>(A)) CHECK(C->dup(A));
   if (!A->isSparse()) return notBuilt("tril of a dense matrix");
   CHECK(C->setStorage(GrB_SPARSE));
